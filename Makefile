@@ -1,0 +1,26 @@
+# Builds libcopra_b200.so (C ABI + sm_100a kernels) in-tree, and the CPU oracle (test infrastructure).
+NVCC ?= nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v
+CSRC := copra_b200/csrc
+OBJS := $(CSRC)/k6_solver.o $(CSRC)/k1_k7_lmpc.o $(CSRC)/capi.o
+LIB := copra_b200/lib/libcopra_b200.so
+HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/copra_b200.h
+
+all: $(LIB) oracle
+
+$(CSRC)/%.o: $(CSRC)/%.cu $(HDRS)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; false)
+
+$(LIB): $(OBJS)
+	mkdir -p copra_b200/lib
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart static
+
+oracle:
+	$(MAKE) -C oracle -s
+
+clean:
+	rm -f $(OBJS) $(CSRC)/*.ptxas.log $(LIB)
+	$(MAKE) -C oracle clean
+
+.PHONY: all oracle clean

@@ -1,0 +1,841 @@
+// capi.cu -- the extern "C" boundary of libcopra_b200.so (include/copra_b200.h).
+// Host-side plumbing only: argument validation (the dimension checks copra performs in
+// initializeCost / initializeConstraint), packing of parameter arrays into one pinned staging
+// buffer + one H2D copy, device workspace management, kernel sequencing, D2H of the results.
+// There is no CPU compute path: every numeric result comes from the sm_100a kernels.
+#include "../../include/copra_b200.h"
+#include "engine.cuh"
+#include "launch.h"
+
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace cb;
+
+namespace {
+
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct Sizes {
+    int X = 0, nU = 0, nvar = 0, meq = 0, mineq = 0, q = 0;
+};
+
+} // namespace
+
+struct copra_b200_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sms = 148;
+    size_t smem_optin = 227 * 1024;
+    int sm_limit = 0;
+    std::string err;
+    long long launches = 0;
+    long long call_launches = 0;
+    std::map<std::string, Buf> dev;
+    Buf pin_in, pin_out;
+    cudaEvent_t ev[8] = {};
+    bool ev_valid[8] = {};
+    cudaEvent_t h2d_done = nullptr; // guards reuse of the pinned upload staging buffer
+    bool h2d_pending = false;
+    // TrajectoryBound line selection cache for DEVICE inputs: (lower ptr, upper ptr, rows) -> lines
+    struct TbKey { const double* lo; const double* up; int rows; bool operator<(const TbKey& o) const { return lo != o.lo ? lo < o.lo : (up != o.up ? up < o.up : rows < o.rows); } };
+    std::map<TbKey, std::pair<std::vector<int>, std::vector<int>>> tb_cache;
+    std::vector<double> sel_host; // last uploaded selector matrices / line lists
+    std::vector<int> lines_host;
+    // state of the last build
+    bool built = false;
+    BuildParams bp{};
+    Sizes sz;
+    double vsmall = 0;
+};
+
+namespace {
+
+int fail(copra_b200_handle* h, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(h, COPRA_B200_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define LAUNCHED(expr)                                                                                              \
+    do {                                                                                                            \
+        int n_ = (expr);                                                                                            \
+        if (n_ < 0) return fail(h, COPRA_B200_E_CUDA, "%s: %s", #expr, cudaGetErrorString(cudaError_t(-n_)));        \
+        h->launches += n_;                                                                                          \
+        h->call_launches += n_;                                                                                     \
+    } while (0)
+
+int dev_reserve(copra_b200_handle* h, const char* name, size_t bytes, void** out)
+{
+    Buf& b = h->dev[name];
+    if (bytes > b.cap) {
+        if (b.p) CU(cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+        size_t cap = bytes + bytes / 8 + 256;
+        CU(cudaMalloc(&b.p, cap));
+        b.cap = cap;
+    }
+    *out = b.p;
+    return 0;
+}
+
+int pin_reserve(copra_b200_handle* h, Buf& b, size_t bytes)
+{
+    if (bytes > b.cap) {
+        if (b.p) CU(cudaFreeHost(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+        size_t cap = bytes + bytes / 8 + 256;
+        CU(cudaMallocHost(&b.p, cap));
+        b.cap = cap;
+    }
+    return 0;
+}
+
+int record(copra_b200_handle* h, int k)
+{
+    if (!h->ev[k]) CU(cudaEventCreate(&h->ev[k]));
+    CU(cudaEventRecord(h->ev[k], h->stream));
+    h->ev_valid[k] = true;
+    return 0;
+}
+
+// ---- staged upload of (ptr, stride) arrays ----------------------------------------------------
+struct Upload {
+    struct Item {
+        copra_b200_array src;
+        size_t size;   // doubles per instance
+        DArr* dst;
+        size_t offset; // doubles into the packed buffer
+        bool shared;
+    };
+    std::vector<Item> items;
+    size_t total = 0;
+    void add(copra_b200_array a, size_t size, DArr* dst)
+    {
+        if (!a.ptr || size == 0) { dst->p = nullptr; dst->s = 0; return; }
+        Item it{ a, size, dst, 0, a.stride == 0 };
+        items.push_back(it);
+    }
+};
+
+int run_upload(copra_b200_handle* h, Upload& U, int batch, int memory, const char* bufname)
+{
+    if (memory == COPRA_B200_DEVICE) {
+        for (auto& it : U.items) { it.dst->p = it.src.ptr; it.dst->s = it.src.stride; }
+        return 0;
+    }
+    size_t total = 0;
+    for (auto& it : U.items) {
+        it.offset = total;
+        total += it.shared ? it.size : it.size * size_t(batch);
+        total = (total + 1) & ~size_t(1); // keep 16-byte alignment
+        if (!it.shared && it.src.stride < (long long)it.size)
+            return fail(h, COPRA_B200_E_ARG, "array stride %lld smaller than its per-instance size %zu", it.src.stride, it.size);
+    }
+    if (total == 0) return 0;
+    int rc = pin_reserve(h, h->pin_in, total * sizeof(double));
+    if (rc) return rc;
+    void* dptr = nullptr;
+    rc = dev_reserve(h, bufname, total * sizeof(double), &dptr);
+    if (rc) return rc;
+    if (h->h2d_pending) { CU(cudaEventSynchronize(h->h2d_done)); h->h2d_pending = false; }
+    double* stage = static_cast<double*>(h->pin_in.p);
+    for (auto& it : U.items) {
+        double* d = stage + it.offset;
+        if (it.shared) std::memcpy(d, it.src.ptr, it.size * sizeof(double));
+        else if (it.src.stride == (long long)it.size) std::memcpy(d, it.src.ptr, it.size * size_t(batch) * sizeof(double));
+        else
+            for (int b = 0; b < batch; ++b) std::memcpy(d + size_t(b) * it.size, it.src.ptr + (long long)b * it.src.stride, it.size * sizeof(double));
+        it.dst->p = static_cast<double*>(dptr) + it.offset;
+        it.dst->s = it.shared ? 0 : (long long)it.size;
+    }
+    CU(cudaMemcpyAsync(dptr, stage, total * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (!h->h2d_done) CU(cudaEventCreateWithFlags(&h->h2d_done, cudaEventDisableTiming));
+    CU(cudaEventRecord(h->h2d_done, h->stream));
+    h->h2d_pending = true;
+    return 0;
+}
+
+// copy a device result to the caller (device->device or device->host through pinned staging)
+struct Download {
+    struct Item {
+        const void* src;
+        void* dst;
+        size_t bytes;
+        size_t offset;
+    };
+    std::vector<Item> items;
+    void add(const void* src, void* dst, size_t bytes)
+    {
+        if (dst && bytes) items.push_back(Item{ src, dst, bytes, 0 });
+    }
+};
+
+int run_download(copra_b200_handle* h, Download& D, int memory)
+{
+    if (D.items.empty()) return 0;
+    if (memory == COPRA_B200_DEVICE) {
+        for (auto& it : D.items)
+            if (it.src != it.dst) CU(cudaMemcpyAsync(it.dst, it.src, it.bytes, cudaMemcpyDeviceToDevice, h->stream));
+        return 0;
+    }
+    size_t total = 0;
+    for (auto& it : D.items) { it.offset = total; total += (it.bytes + 15) & ~size_t(15); }
+    int rc = pin_reserve(h, h->pin_out, total);
+    if (rc) return rc;
+    char* stage = static_cast<char*>(h->pin_out.p);
+    for (auto& it : D.items) CU(cudaMemcpyAsync(stage + it.offset, it.src, it.bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (auto& it : D.items) std::memcpy(it.dst, stage + it.offset, it.bytes);
+    return 0;
+}
+
+// ---- problem description -> families ----------------------------------------------------------
+struct Plan {
+    Sizes sz;
+    struct CostMeta { int kind, rows, i0, i1, hasM, hasN; };
+    struct FamMeta { int cstr, rows, i0, i1, hasE, hasG, is_eq, row_off, which; std::vector<int> lines; };
+    std::vector<CostMeta> costs;
+    std::vector<FamMeta> fams;
+    int bound_cstr = -1;
+};
+
+int fetch_host(copra_b200_handle* h, const copra_b200_array& a, int count, int memory, std::vector<double>& out)
+{
+    out.resize(count);
+    if (memory == COPRA_B200_HOST) std::memcpy(out.data(), a.ptr, sizeof(double) * count);
+    else {
+        CU(cudaMemcpyAsync(out.data(), a.ptr, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+int make_plan(copra_b200_handle* h, const copra_b200_problem* p, Plan& pl)
+{
+    if (!p) return fail(h, COPRA_B200_E_ARG, "null problem");
+    if (p->nx <= 0 || p->nu <= 0 || p->batch <= 0) return fail(h, COPRA_B200_E_ARG, "nx, nu and batch must be positive");
+    if (p->N <= 0) return fail(h, COPRA_B200_E_ARG, "The number of step sould be a positive number!"); // PreviewSystem.cpp:31-33
+    if (!p->A.ptr || !p->B.ptr || !p->d.ptr || !p->x0.ptr) return fail(h, COPRA_B200_E_ARG, "A, B, d and x0 are required");
+    if (p->ncost < 0 || p->ncost > kMaxCost) return fail(h, COPRA_B200_E_ARG, "at most %d cost functions", kMaxCost);
+    if (p->memory != COPRA_B200_HOST && p->memory != COPRA_B200_DEVICE) return fail(h, COPRA_B200_E_ARG, "bad memory kind");
+    const int nx = p->nx, nu = p->nu, N = p->N;
+    pl.sz.X = nx * (N + 1);
+    pl.sz.nU = nu * N;
+    pl.sz.nvar = p->initial_state ? nx + pl.sz.nU : pl.sz.nU;
+    for (int i = 0; i < p->ncost; ++i) {
+        const copra_b200_cost& c = p->costs[i];
+        if (c.rows <= 0 || !c.p.ptr) return fail(h, COPRA_B200_E_ARG, "cost %d: rows must be positive and p given", i);
+        Plan::CostMeta m{ c.kind, c.rows, 0, 0, 0, 0 };
+        switch (c.kind) {
+        case COPRA_B200_COST_TRAJECTORY: m.i0 = 0; m.i1 = N + 1; m.hasM = 1; break;
+        case COPRA_B200_COST_TARGET: m.i0 = N; m.i1 = N + 1; m.hasM = 1; break;
+        case COPRA_B200_COST_CONTROL: m.i0 = 0; m.i1 = N; m.hasN = 1; break;
+        case COPRA_B200_COST_MIXED: m.i0 = 0; m.i1 = N; m.hasM = 1; m.hasN = 1; break;
+        default: return fail(h, COPRA_B200_E_ARG, "cost %d: unknown kind %d", i, c.kind);
+        }
+        if (m.hasM && !c.M.ptr) return fail(h, COPRA_B200_E_ARG, "cost %d: M is required", i);
+        if (m.hasN && !c.N.ptr) return fail(h, COPRA_B200_E_ARG, "cost %d: N is required", i);
+        if (!c.w.ptr) return fail(h, COPRA_B200_E_ARG, "cost %d: weights are required (copra default: ones)", i);
+        pl.costs.push_back(m);
+    }
+    int eq_off = 0, in_off = 0;
+    for (int i = 0; i < p->ncstr; ++i) {
+        const copra_b200_constraint& c = p->cstrs[i];
+        if (c.rows <= 0) return fail(h, COPRA_B200_E_ARG, "constraint %d: rows must be positive", i);
+        auto push = [&](int i0, int i1, int hasE, int hasG, bool iseq, int which, std::vector<int> lines) {
+            Plan::FamMeta f;
+            f.cstr = i; f.rows = lines.empty() ? c.rows : int(lines.size());
+            f.i0 = i0; f.i1 = i1; f.hasE = hasE; f.hasG = hasG; f.is_eq = iseq ? 1 : 0; f.which = which;
+            f.lines = std::move(lines);
+            int& off = iseq ? eq_off : in_off;
+            f.row_off = off;
+            off += f.rows * (i1 - i0);
+            pl.fams.push_back(f);
+        };
+        switch (c.kind) {
+        case COPRA_B200_CSTR_TRAJECTORY:
+            if (!c.E.ptr || !c.f.ptr) return fail(h, COPRA_B200_E_ARG, "constraint %d: E and f are required", i);
+            push(0, N + 1, 1, 0, !c.is_ineq, 0, {});
+            break;
+        case COPRA_B200_CSTR_CONTROL:
+            if (!c.G.ptr || !c.f.ptr) return fail(h, COPRA_B200_E_ARG, "constraint %d: G and f are required", i);
+            push(0, N, 0, 1, !c.is_ineq, 0, {});
+            break;
+        case COPRA_B200_CSTR_MIXED:
+            if (!c.E.ptr || !c.G.ptr || !c.f.ptr) return fail(h, COPRA_B200_E_ARG, "constraint %d: E, G and f are required", i);
+            push(0, N, 1, 1, !c.is_ineq, 0, {});
+            break;
+        case COPRA_B200_CSTR_TRAJECTORY_BOUND: {
+            if (!c.lower.ptr || !c.upper.ptr) return fail(h, COPRA_B200_E_ARG, "constraint %d: lower and upper are required", i);
+            if (c.rows != nx) return fail(h, COPRA_B200_E_ARG, "constraint %d: trajectory bounds must have nx rows (step-size entry)", i);
+            // line selection (include/constraints.h:247-254) is part of the problem SHAPE: it is taken
+            // from instance 0 and, for host inputs, verified to be the same for every instance.
+            std::vector<int> ll, ul;
+            copra_b200_handle::TbKey key{ c.lower.ptr, c.upper.ptr, nx };
+            auto hit = h->tb_cache.find(key);
+            if (p->memory == COPRA_B200_DEVICE && hit != h->tb_cache.end()) {
+                ll = hit->second.first;
+                ul = hit->second.second;
+            } else {
+                std::vector<double> lo, up;
+                int rc = fetch_host(h, c.lower, nx, p->memory, lo);
+                if (rc) return rc;
+                rc = fetch_host(h, c.upper, nx, p->memory, up);
+                if (rc) return rc;
+                for (int l = 0; l < nx; ++l) if (lo[l] != -INFINITY) ll.push_back(l);
+                for (int l = 0; l < nx; ++l) if (up[l] != INFINITY) ul.push_back(l);
+                if (p->memory == COPRA_B200_HOST) {
+                    for (int b = 1; b < p->batch; ++b)
+                        for (int l = 0; l < nx; ++l) {
+                            const double a = c.lower.ptr[(long long)b * c.lower.stride + l], u = c.upper.ptr[(long long)b * c.upper.stride + l];
+                            if ((a != -INFINITY) != (lo[l] != -INFINITY) || (u != INFINITY) != (up[l] != INFINITY))
+                                return fail(h, COPRA_B200_E_ARG, "constraint %d: the set of infinite trajectory bounds must be the same for every instance", i);
+                        }
+                } else h->tb_cache[key] = std::make_pair(ll, ul);
+            }
+            if (!ll.empty()) push(0, N + 1, 1, 0, false, 1, ll);
+            if (!ul.empty()) push(0, N + 1, 1, 0, false, 2, ul);
+        } break;
+        case COPRA_B200_CSTR_CONTROL_BOUND:
+            if (!c.lower.ptr || !c.upper.ptr) return fail(h, COPRA_B200_E_ARG, "constraint %d: lower and upper are required", i);
+            if (c.rows != nu) return fail(h, COPRA_B200_E_ARG, "constraint %d: control bounds must have nu rows (step-size entry)", i);
+            if (pl.bound_cstr >= 0) return fail(h, COPRA_B200_E_UNSUPPORTED, "only one ControlBoundConstraint per controller (reference quirk Q8)");
+            pl.bound_cstr = i;
+            break;
+        default: return fail(h, COPRA_B200_E_ARG, "constraint %d: unknown kind %d", i, c.kind);
+        }
+    }
+    if (int(pl.fams.size()) > kMaxFam) return fail(h, COPRA_B200_E_ARG, "too many constraint families");
+    pl.sz.meq = eq_off;
+    pl.sz.mineq = in_off;
+    pl.sz.q = eq_off + in_off + 2 * pl.sz.nvar;
+    return 0;
+}
+
+template <class T> int ws(copra_b200_handle* h, const char* name, size_t count, T** out)
+{
+    void* p = nullptr;
+    int rc = dev_reserve(h, name, std::max<size_t>(count, 1) * sizeof(T), &p);
+    *out = static_cast<T*>(p);
+    return rc;
+}
+
+int do_build(copra_b200_handle* h, const copra_b200_problem* p)
+{
+    Plan pl;
+    int rc = make_plan(h, p, pl);
+    if (rc) return rc;
+    if (p->batch > 65535) return fail(h, COPRA_B200_E_UNSUPPORTED, "batch > 65535 per call: shard the batch (bench.py does)");
+    CU(cudaSetDevice(h->device));
+    h->call_launches = 0;
+    for (bool& v : h->ev_valid) v = false;
+    rc = record(h, 0);
+    if (rc) return rc;
+
+    BuildParams& P = h->bp;
+    std::memset(&P, 0, sizeof P);
+    const int nx = p->nx, nu = p->nu, N = p->N, B = p->batch;
+    P.nx = nx; P.nu = nu; P.N = N; P.batch = B;
+    P.X = pl.sz.X; P.nU = pl.sz.nU; P.nvar = pl.sz.nvar; P.meq = pl.sz.meq; P.mineq = pl.sz.mineq;
+    P.initial_state = p->initial_state ? 1 : 0;
+    P.ncost = int(pl.costs.size());
+    P.nfam = int(pl.fams.size());
+
+    // selector matrices + line indices for TrajectoryBound families (tiny, shared by all instances)
+    std::vector<double> sel;
+    std::vector<int> lines;
+    std::vector<size_t> sel_off(pl.fams.size(), 0), line_off(pl.fams.size(), 0);
+    for (size_t k = 0; k < pl.fams.size(); ++k) {
+        const auto& f = pl.fams[k];
+        if (f.which == 0) continue;
+        sel_off[k] = sel.size();
+        line_off[k] = lines.size();
+        sel.resize(sel.size() + size_t(f.rows) * nx, 0.0);
+        for (int l = 0; l < f.rows; ++l) {
+            sel[sel_off[k] + l + size_t(f.lines[l]) * f.rows] = 1.0;
+            lines.push_back(f.lines[l]);
+        }
+    }
+    double* d_sel = nullptr;
+    int* d_lines = nullptr;
+    if (!sel.empty()) {
+        rc = ws(h, "sel", sel.size(), &d_sel); if (rc) return rc;
+        rc = ws(h, "lines", lines.size(), &d_lines); if (rc) return rc;
+        if (sel != h->sel_host || lines != h->lines_host) {
+            CU(cudaStreamSynchronize(h->stream)); // previous kernels may still read the old selectors
+            h->sel_host = sel;
+            h->lines_host = lines;
+            CU(cudaMemcpyAsync(d_sel, h->sel_host.data(), sel.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            CU(cudaMemcpyAsync(d_lines, h->lines_host.data(), lines.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+        }
+    }
+
+    // parameters
+    Upload U;
+    U.add(p->A, size_t(nx) * nx, &P.A);
+    U.add(p->B, size_t(nx) * nu, &P.B);
+    U.add(p->d, nx, &P.d);
+    U.add(p->x0, nx, &P.x0);
+    if (p->initial_state) {
+        U.add(p->R, size_t(nx) * nx, &P.R);
+        U.add(p->r, nx, &P.r);
+        U.add(p->x0lb, nx, &P.x0lb);
+        U.add(p->x0ub, nx, &P.x0ub);
+    }
+    for (int i = 0; i < P.ncost; ++i) {
+        const copra_b200_cost& c = p->costs[i];
+        CostFam& F = P.cost[i];
+        F.rows = c.rows; F.i0 = pl.costs[i].i0; F.i1 = pl.costs[i].i1; F.hasM = pl.costs[i].hasM; F.hasN = pl.costs[i].hasN;
+        if (F.hasM) U.add(c.M, size_t(c.rows) * nx, &F.M);
+        if (F.hasN) U.add(c.N, size_t(c.rows) * nu, &F.N);
+        U.add(c.p, c.rows, &F.p);
+        U.add(c.w, c.rows, &F.w);
+    }
+    // trajectory-bound families share the uploaded lower / upper vectors of their constraint
+    std::vector<DArr> lowerArr(p->ncstr), upperArr(p->ncstr);
+    for (int i = 0; i < p->ncstr; ++i) {
+        const copra_b200_constraint& c = p->cstrs[i];
+        if (c.kind == COPRA_B200_CSTR_TRAJECTORY_BOUND || c.kind == COPRA_B200_CSTR_CONTROL_BOUND) {
+            U.add(c.lower, c.rows, &lowerArr[i]);
+            U.add(c.upper, c.rows, &upperArr[i]);
+        }
+    }
+    for (int k = 0; k < P.nfam; ++k) {
+        const auto& f = pl.fams[k];
+        const copra_b200_constraint& c = p->cstrs[f.cstr];
+        CstrFam& F = P.fam[k];
+        F.rows = f.rows; F.i0 = f.i0; F.i1 = f.i1; F.hasE = f.hasE; F.hasG = f.hasG; F.is_eq = f.is_eq; F.row_off = f.row_off;
+        F.fidx = nullptr;
+        if (f.which == 0) {
+            if (f.hasE) U.add(c.E, size_t(c.rows) * nx, &F.E);
+            if (f.hasG) U.add(c.G, size_t(c.rows) * nu, &F.G);
+            U.add(c.f, c.rows, &F.f);
+        }
+    }
+    rc = run_upload(h, U, B, p->memory, "params");
+    if (rc) return rc;
+    for (int k = 0; k < P.nfam; ++k) {
+        const auto& f = pl.fams[k];
+        if (f.which == 0) continue;
+        CstrFam& F = P.fam[k];
+        F.E.p = d_sel + sel_off[k];
+        F.E.s = 0;
+        F.f = f.which == 1 ? lowerArr[f.cstr] : upperArr[f.cstr];
+        F.fidx = d_lines + line_off[k];
+    }
+    if (pl.bound_cstr >= 0) {
+        P.cb_lower = lowerArr[pl.bound_cstr];
+        P.cb_upper = upperArr[pl.bound_cstr];
+    }
+    rc = record(h, 1);
+    if (rc) return rc;
+
+    // workspace
+    const size_t X = P.X, nU = P.nU, nv = P.nvar, meq = P.meq, m = P.mineq, Bz = B;
+    if ((rc = ws(h, "Phi", Bz * X * nx, &P.Phi))) return rc;
+    if ((rc = ws(h, "Gs", Bz * size_t(N) * nx * nu, &P.Gs))) return rc;
+    if ((rc = ws(h, "xi", Bz * X, &P.xi))) return rc;
+    if ((rc = ws(h, "Q", Bz * nv * nv, &P.Q))) return rc;
+    if ((rc = ws(h, "c", Bz * nv, &P.c))) return rc;
+    if ((rc = ws(h, "Aeq", Bz * meq * nv, &P.Aeq))) return rc;
+    if ((rc = ws(h, "beq", Bz * meq, &P.beq))) return rc;
+    if ((rc = ws(h, "Aineq", Bz * m * nv, &P.Aineq))) return rc;
+    if ((rc = ws(h, "bineq", Bz * m, &P.bineq))) return rc;
+    if ((rc = ws(h, "lb", Bz * nv, &P.lb))) return rc;
+    if ((rc = ws(h, "ub", Bz * nv, &P.ub))) return rc;
+    if ((rc = ws(h, "Yeq", Bz * meq * nx, &P.Yeq))) return rc;
+    if ((rc = ws(h, "zeq", Bz * meq, &P.zeq))) return rc;
+    if ((rc = ws(h, "Yin", Bz * m * nx, &P.Yin))) return rc;
+    if ((rc = ws(h, "zin", Bz * m, &P.zin))) return rc;
+    for (int i = 0; i < P.ncost; ++i) {
+        CostFam& F = P.cost[i];
+        const size_t r = F.rows, ns = F.i1 - F.i0;
+        char nm[32];
+        F.sMGx = r * nu * (N + 1); F.sMPhi = r * nx * ns; F.sres = r * ns; F.sE = size_t(nx) * nU; F.sf = nU;
+        snprintf(nm, sizeof nm, "MGx%d", i); if ((rc = ws(h, nm, Bz * F.sMGx, &F.MGx))) return rc;
+        snprintf(nm, sizeof nm, "MPhi%d", i); if ((rc = ws(h, nm, Bz * F.sMPhi, &F.MPhi))) return rc;
+        snprintf(nm, sizeof nm, "res%d", i); if ((rc = ws(h, nm, Bz * F.sres, &F.res))) return rc;
+        snprintf(nm, sizeof nm, "Ec%d", i); if ((rc = ws(h, nm, Bz * F.sE, &F.E))) return rc;
+        snprintf(nm, sizeof nm, "fc%d", i); if ((rc = ws(h, nm, Bz * F.sf, &F.f))) return rc;
+    }
+    for (int k = 0; k < P.nfam; ++k) {
+        CstrFam& F = P.fam[k];
+        char nm[32];
+        F.sEGx = size_t(F.rows) * nu * (N + 1);
+        snprintf(nm, sizeof nm, "EGx%d", k);
+        if ((rc = ws(h, nm, Bz * F.sEGx, &F.EGx))) return rc;
+    }
+    double* schur = nullptr;
+    long long schur_stride = 0;
+    if (P.initial_state) {
+        schur_stride = (long long)odd_ld(P.nU) * P.nU;
+        if ((rc = ws(h, "schur", size_t(h->sms) * 8 * schur_stride, &schur))) return rc;
+    }
+
+    LAUNCHED(k1_condense_launch(P, h->stream));
+    if ((rc = record(h, 2))) return rc;
+    LAUNCHED(k2k4_assemble_launch(P, schur, schur_stride, h->sms, h->smem_optin, h->stream));
+    if ((rc = record(h, 3))) return rc;
+    h->sz = pl.sz;
+    h->built = true;
+    return 0;
+}
+
+int do_solve(copra_b200_handle* h, const copra_b200_results* r)
+{
+    if (!h->built) return fail(h, COPRA_B200_E_STATE, "copra_b200_lmpc_solve called before a successful build");
+    const BuildParams& P = h->bp;
+    const size_t B = P.batch, nv = P.nvar;
+    int rc;
+    double *x = nullptr, *control = nullptr, *traj = nullptr;
+    int *status = nullptr, *iters = nullptr, *nact = nullptr, *iact = nullptr, *counter = nullptr;
+    const bool devres = r && r->memory == COPRA_B200_DEVICE;
+    if ((rc = ws(h, "res_x", B * nv, &x))) return rc;
+    if ((rc = ws(h, "res_control", B * P.nU, &control))) return rc;
+    if ((rc = ws(h, "res_traj", B * P.X, &traj))) return rc;
+    if ((rc = ws(h, "res_status", B, &status))) return rc;
+    if ((rc = ws(h, "res_iters", 2 * B, &iters))) return rc;
+    if ((rc = ws(h, "res_nact", B, &nact))) return rc;
+    if ((rc = ws(h, "res_iact", B * nv, &iact))) return rc;
+    if ((rc = ws(h, "counter", 1, &counter))) return rc;
+    if (devres) { // write straight into the caller's device buffers where given
+        if (r->x) x = r->x;
+        if (r->control) control = r->control;
+        if (r->trajectory) traj = r->trajectory;
+        if (r->status) status = r->status;
+        if (r->iters) iters = r->iters;
+        if (r->nact) nact = r->nact;
+        if (r->iact) iact = r->iact;
+    }
+    const int sms = h->sm_limit > 0 ? std::min(h->sm_limit, h->sms) : h->sms;
+    GiPlan plan = gi_plan(P.nvar, P.meq, P.mineq, P.batch, sms, h->smem_optin);
+    GiBatch G{};
+    G.n = P.nvar; G.meq = P.meq; G.m = P.mineq; G.batch = P.batch;
+    G.Q = DArr{ P.Q, (long long)(nv * nv) };
+    G.c = DArr{ P.c, (long long)nv };
+    G.Aeq = DArr{ P.meq ? P.Aeq : nullptr, (long long)(size_t(P.meq) * nv) };
+    G.beq = DArr{ P.meq ? P.beq : nullptr, P.meq };
+    G.Aineq = DArr{ P.mineq ? P.Aineq : nullptr, (long long)(size_t(P.mineq) * nv) };
+    G.bineq = DArr{ P.mineq ? P.bineq : nullptr, P.mineq };
+    G.lb = DArr{ P.lb, (long long)nv };
+    G.ub = DArr{ P.ub, (long long)nv };
+    G.x = x; G.status = status; G.iters = iters; G.nact = nact; G.iact = iact;
+    G.counter = counter;
+    G.vsmall = h->vsmall;
+    G.max_iter = 50 * (P.meq + P.mineq + 2 * P.nvar) + 100;
+    G.j_smem = plan.j_smem; G.s_smem = plan.s_smem; G.a_smem = plan.a_smem;
+    G.ws = nullptr; G.ws_stride = plan.ws_stride;
+    if (plan.ws_stride > 0 && (rc = ws(h, "gi_ws", size_t(plan.grid) * plan.ws_stride, &G.ws))) return rc;
+    CU(cudaMemsetAsync(counter, 0, sizeof(int), h->stream));
+    cudaError_t e = gi_launch(G, plan, h->stream);
+    if (e != cudaSuccess) return fail(h, COPRA_B200_E_CUDA, "gi_launch: %s", cudaGetErrorString(e));
+    h->launches += 1; h->call_launches += 1;
+    if ((rc = record(h, 4))) return rc;
+    const bool want_ct = !r || r->control || r->trajectory;
+    if (want_ct) LAUNCHED(k7_results_launch(P, x, control, traj, h->stream));
+    if ((rc = record(h, 5))) return rc;
+    if (r && !devres) {
+        Download D;
+        D.add(x, r->x, B * nv * sizeof(double));
+        D.add(control, r->control, B * P.nU * sizeof(double));
+        D.add(traj, r->trajectory, B * P.X * sizeof(double));
+        D.add(status, r->status, B * sizeof(int));
+        D.add(iters, r->iters, 2 * B * sizeof(int));
+        D.add(nact, r->nact, B * sizeof(int));
+        D.add(iact, r->iact, B * nv * sizeof(int));
+        if ((rc = run_download(h, D, COPRA_B200_HOST))) return rc;
+    }
+    if ((rc = record(h, 6))) return rc;
+    return 0;
+}
+
+} // namespace
+
+// ===============================================================================================
+extern "C" {
+
+int copra_b200_abi_version(void) { return COPRA_B200_ABI_VERSION; }
+
+int copra_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int copra_b200_create(const copra_b200_options* opt, copra_b200_handle** out)
+{
+    if (!out) return COPRA_B200_E_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return COPRA_B200_E_NOGPU;
+    const int dev = opt ? opt->device : 0;
+    if (dev < 0 || dev >= n) return COPRA_B200_E_ARG;
+    if (cudaSetDevice(dev) != cudaSuccess) return COPRA_B200_E_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return COPRA_B200_E_CUDA;
+    if (prop.major < 10) return COPRA_B200_E_NOGPU; // kernels are built for sm_100a only
+    copra_b200_handle* h = new copra_b200_handle();
+    h->device = dev;
+    h->sms = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    h->sm_limit = opt ? opt->sm_limit : 0;
+    h->vsmall = gi_vsmall();
+    if (opt && opt->stream) h->stream = static_cast<cudaStream_t>(opt->stream);
+    else {
+        if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return COPRA_B200_E_CUDA; }
+        h->own_stream = true;
+    }
+    *out = h;
+    return COPRA_B200_OK;
+}
+
+void copra_b200_destroy(copra_b200_handle* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (auto& kv : h->dev) if (kv.second.p) cudaFree(kv.second.p);
+    if (h->pin_in.p) cudaFreeHost(h->pin_in.p);
+    if (h->pin_out.p) cudaFreeHost(h->pin_out.p);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->h2d_done) cudaEventDestroy(h->h2d_done);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char* copra_b200_last_error(const copra_b200_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int copra_b200_set_stream(copra_b200_handle* h, void* s)
+{
+    if (!h) return COPRA_B200_E_ARG;
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+    h->stream = static_cast<cudaStream_t>(s);
+    return 0;
+}
+
+int copra_b200_synchronize(copra_b200_handle* h)
+{
+    if (!h) return COPRA_B200_E_ARG;
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+long long copra_b200_launch_count(const copra_b200_handle* h) { return h ? h->launches : 0; }
+
+int copra_b200_last_timing(const copra_b200_handle* hc, copra_b200_timing* t)
+{
+    copra_b200_handle* h = const_cast<copra_b200_handle*>(hc);
+    if (!h || !t) return COPRA_B200_E_ARG;
+    std::memset(t, 0, sizeof *t);
+    CU(cudaStreamSynchronize(h->stream));
+    auto span = [&](int a, int b) -> float {
+        float ms = 0.f;
+        if (h->ev_valid[a] && h->ev_valid[b]) cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]);
+        return ms;
+    };
+    t->h2d_ms = span(0, 1); t->condense_ms = span(1, 2); t->assemble_ms = span(2, 3); t->solve_ms = span(3, 4);
+    t->rollout_ms = span(4, 5); t->d2h_ms = span(5, 6); t->total_ms = span(0, 6);
+    t->launches = h->call_launches;
+    return 0;
+}
+
+int copra_b200_lmpc_sizes(copra_b200_handle* h, const copra_b200_problem* p, copra_b200_sizes* s)
+{
+    if (!h || !s) return COPRA_B200_E_ARG;
+    Plan pl;
+    int rc = make_plan(h, p, pl);
+    if (rc) return rc;
+    s->X = pl.sz.X; s->nU = pl.sz.nU; s->nvar = pl.sz.nvar; s->meq = pl.sz.meq; s->mineq = pl.sz.mineq; s->q = pl.sz.q;
+    return 0;
+}
+
+int copra_b200_lmpc_build(copra_b200_handle* h, const copra_b200_problem* p)
+{
+    if (!h) return COPRA_B200_E_ARG;
+    h->built = false;
+    return do_build(h, p);
+}
+
+int copra_b200_lmpc_solve(copra_b200_handle* h, const copra_b200_results* r)
+{
+    if (!h) return COPRA_B200_E_ARG;
+    return do_solve(h, r);
+}
+
+int copra_b200_lmpc_run(copra_b200_handle* h, const copra_b200_problem* p, const copra_b200_results* r)
+{
+    if (!h) return COPRA_B200_E_ARG;
+    h->built = false;
+    int rc = do_build(h, p);
+    if (rc) return rc;
+    return do_solve(h, r);
+}
+
+int copra_b200_lmpc_download(copra_b200_handle* h, int what, double* out, int memory)
+{
+    if (!h || !out) return COPRA_B200_E_ARG;
+    if (!h->built) return fail(h, COPRA_B200_E_STATE, "download before build");
+    const BuildParams& P = h->bp;
+    const size_t B = P.batch, nv = P.nvar;
+    const double* src = nullptr;
+    size_t count = 0;
+    switch (what) {
+    case COPRA_B200_GET_PHI: src = P.Phi; count = B * P.X * P.nx; break;
+    case COPRA_B200_GET_XI: src = P.xi; count = B * P.X; break;
+    case COPRA_B200_GET_Q: src = P.Q; count = B * nv * nv; break;
+    case COPRA_B200_GET_C: src = P.c; count = B * nv; break;
+    case COPRA_B200_GET_AEQ: src = P.Aeq; count = B * P.meq * nv; break;
+    case COPRA_B200_GET_BEQ: src = P.beq; count = B * P.meq; break;
+    case COPRA_B200_GET_AINEQ: src = P.Aineq; count = B * P.mineq * nv; break;
+    case COPRA_B200_GET_BINEQ: src = P.bineq; count = B * P.mineq; break;
+    case COPRA_B200_GET_LB: src = P.lb; count = B * nv; break;
+    case COPRA_B200_GET_UB: src = P.ub; count = B * nv; break;
+    case COPRA_B200_GET_PSI: {
+        count = B * size_t(P.X) * P.nU;
+        double* psi = nullptr;
+        if (memory == COPRA_B200_DEVICE) psi = out;
+        else { int rc = ws(h, "Psi", count, &psi); if (rc) return rc; }
+        LAUNCHED(k1_psi_fill_launch(P.Gs, (long long)P.N * P.nx * P.nu, psi, P.nx, P.nu, P.N, P.batch, h->stream));
+        if (memory == COPRA_B200_DEVICE) return 0;
+        src = psi;
+    } break;
+    default: return fail(h, COPRA_B200_E_ARG, "unknown download id %d", what);
+    }
+    if (count == 0) return 0;
+    if (memory == COPRA_B200_DEVICE) CU(cudaMemcpyAsync(out, src, count * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    else {
+        CU(cudaMemcpyAsync(out, src, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+int copra_b200_condense(copra_b200_handle* h, int nx, int nu, int N, int batch, copra_b200_array A, copra_b200_array B,
+    copra_b200_array d, double* Phi, double* Psi, double* xi, int memory)
+{
+    if (!h) return COPRA_B200_E_ARG;
+    if (nx <= 0 || nu <= 0 || batch <= 0) return fail(h, COPRA_B200_E_ARG, "nx, nu and batch must be positive");
+    if (N <= 0) return fail(h, COPRA_B200_E_ARG, "The number of step sould be a positive number!");
+    if (!A.ptr || !B.ptr || !d.ptr) return fail(h, COPRA_B200_E_ARG, "A, B and d are required");
+    CU(cudaSetDevice(h->device));
+    h->call_launches = 0;
+    h->built = false;
+    BuildParams P{};
+    P.nx = nx; P.nu = nu; P.N = N; P.batch = batch; P.X = nx * (N + 1); P.nU = nu * N; P.nvar = P.nU;
+    Upload U;
+    U.add(A, size_t(nx) * nx, &P.A);
+    U.add(B, size_t(nx) * nu, &P.B);
+    U.add(d, nx, &P.d);
+    int rc = run_upload(h, U, batch, memory, "params");
+    if (rc) return rc;
+    const size_t Bz = batch, X = P.X;
+    const bool dv = memory == COPRA_B200_DEVICE;
+    if (dv && Phi) P.Phi = Phi; else if ((rc = ws(h, "Phi", Bz * X * nx, &P.Phi))) return rc;
+    if (dv && xi) P.xi = xi; else if ((rc = ws(h, "xi", Bz * X, &P.xi))) return rc;
+    if ((rc = ws(h, "Gs", Bz * size_t(N) * nx * nu, &P.Gs))) return rc;
+    LAUNCHED(k1_condense_launch(P, h->stream));
+    double* psi = nullptr;
+    if (Psi) {
+        if (dv) psi = Psi; else if ((rc = ws(h, "Psi", Bz * X * P.nU, &psi))) return rc;
+        LAUNCHED(k1_psi_fill_launch(P.Gs, (long long)N * nx * nu, psi, nx, nu, N, batch, h->stream));
+    }
+    if (!dv) {
+        if (Phi) CU(cudaMemcpyAsync(Phi, P.Phi, Bz * X * nx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (xi) CU(cudaMemcpyAsync(xi, P.xi, Bz * X * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (Psi) CU(cudaMemcpyAsync(Psi, psi, Bz * X * P.nU * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+int copra_b200_solve_qp_batch(copra_b200_handle* h, int n, int meq, int m, int batch, copra_b200_array Q, copra_b200_array c,
+    copra_b200_array Aeq, copra_b200_array beq, copra_b200_array Aineq, copra_b200_array bineq, copra_b200_array lb,
+    copra_b200_array ub, double* x, int* status, int* iters, int* nact, int* iact, int memory)
+{
+    if (!h) return COPRA_B200_E_ARG;
+    if (n <= 0 || meq < 0 || m < 0 || batch <= 0) return fail(h, COPRA_B200_E_ARG, "bad QP dimensions");
+    if (!Q.ptr || !c.ptr || !lb.ptr || !ub.ptr) return fail(h, COPRA_B200_E_ARG, "Q, c, lb and ub are required");
+    if ((meq > 0 && (!Aeq.ptr || !beq.ptr)) || (m > 0 && (!Aineq.ptr || !bineq.ptr))) return fail(h, COPRA_B200_E_ARG, "constraint matrices missing");
+    CU(cudaSetDevice(h->device));
+    h->call_launches = 0;
+    h->built = false;
+    for (bool& v : h->ev_valid) v = false;
+    int rc = record(h, 0);
+    if (rc) return rc;
+    GiBatch G{};
+    G.n = n; G.meq = meq; G.m = m; G.batch = batch;
+    Upload U;
+    U.add(Q, size_t(n) * n, &G.Q);
+    U.add(c, n, &G.c);
+    if (meq) { U.add(Aeq, size_t(meq) * n, &G.Aeq); U.add(beq, meq, &G.beq); }
+    if (m) { U.add(Aineq, size_t(m) * n, &G.Aineq); U.add(bineq, m, &G.bineq); }
+    U.add(lb, n, &G.lb);
+    U.add(ub, n, &G.ub);
+    if ((rc = run_upload(h, U, batch, memory, "qp_params"))) return rc;
+    if ((rc = record(h, 1))) return rc;
+    h->ev_valid[2] = h->ev_valid[3] = false;
+    const size_t B = batch;
+    const bool dv = memory == COPRA_B200_DEVICE;
+    int* counter = nullptr;
+    if (dv && x) G.x = x; else if ((rc = ws(h, "res_x", B * n, &G.x))) return rc;
+    if (dv && status) G.status = status; else if ((rc = ws(h, "res_status", B, &G.status))) return rc;
+    if (dv && iters) G.iters = iters; else if ((rc = ws(h, "res_iters", 2 * B, &G.iters))) return rc;
+    if (dv && nact) G.nact = nact; else if ((rc = ws(h, "res_nact", B, &G.nact))) return rc;
+    if (dv && iact) G.iact = iact; else if ((rc = ws(h, "res_iact", B * n, &G.iact))) return rc;
+    if ((rc = ws(h, "counter", 1, &counter))) return rc;
+    const int sms = h->sm_limit > 0 ? std::min(h->sm_limit, h->sms) : h->sms;
+    GiPlan plan = gi_plan(n, meq, m, batch, sms, h->smem_optin);
+    G.counter = counter;
+    G.vsmall = h->vsmall;
+    G.max_iter = 50 * (meq + m + 2 * n) + 100;
+    G.j_smem = plan.j_smem; G.s_smem = plan.s_smem; G.a_smem = plan.a_smem;
+    G.ws_stride = plan.ws_stride;
+    if (plan.ws_stride > 0 && (rc = ws(h, "gi_ws", size_t(plan.grid) * plan.ws_stride, &G.ws))) return rc;
+    CU(cudaMemsetAsync(counter, 0, sizeof(int), h->stream));
+    if ((rc = record(h, 3))) return rc;
+    cudaError_t e = gi_launch(G, plan, h->stream);
+    if (e != cudaSuccess) return fail(h, COPRA_B200_E_CUDA, "gi_launch: %s", cudaGetErrorString(e));
+    h->launches += 1; h->call_launches += 1;
+    if ((rc = record(h, 4))) return rc;
+    if ((rc = record(h, 5))) return rc;
+    if (!dv) {
+        Download D;
+        D.add(G.x, x, B * n * sizeof(double));
+        D.add(G.status, status, B * sizeof(int));
+        D.add(G.iters, iters, 2 * B * sizeof(int));
+        D.add(G.nact, nact, B * sizeof(int));
+        D.add(G.iact, iact, B * n * sizeof(int));
+        if ((rc = run_download(h, D, COPRA_B200_HOST))) return rc;
+    }
+    if ((rc = record(h, 6))) return rc;
+    return 0;
+}
+
+} // extern "C"

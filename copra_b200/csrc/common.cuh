@@ -1,0 +1,90 @@
+// common.cuh -- shared helpers for the copra_b200 CUDA kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace cb {
+
+constexpr int kWarp = 32;
+constexpr int kMaxWarps = 32;
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// (value, index) arg-min with strict '<' on value and lowest index on ties (qpgen2's forward scans).
+struct MinIdx {
+    double v;
+    int i;
+};
+__device__ __forceinline__ MinIdx better(MinIdx a, MinIdx b)
+{
+    if (b.i >= 0 && (a.i < 0 || b.v < a.v || (b.v == a.v && b.i < a.i))) return b;
+    return a;
+}
+__device__ __forceinline__ MinIdx warp_argmin(MinIdx m)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        MinIdx t;
+        t.v = __shfl_xor_sync(0xffffffffu, m.v, o);
+        t.i = __shfl_xor_sync(0xffffffffu, m.i, o);
+        m = better(m, t);
+    }
+    return m;
+}
+
+// Block-wide reductions through a small smem scratch (>= kMaxWarps entries each).  All threads
+// must call; result is returned to every thread.  Ends with a __syncthreads so scratch is reusable.
+__device__ __forceinline__ double block_sum(double v, double* scratch)
+{
+    v = warp_sum(v);
+    const int nw = (blockDim.x + 31) >> 5;
+    if (lane_id() == 0) scratch[warp_id()] = v;
+    __syncthreads();
+    double t = (lane_id() < nw) ? scratch[lane_id()] : 0.0;
+    t = warp_sum(t);
+    __syncthreads();
+    return t;
+}
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* scratch)
+{
+    a = warp_sum(a);
+    b = warp_sum(b);
+    const int nw = (blockDim.x + 31) >> 5;
+    if (lane_id() == 0) {
+        scratch[warp_id()] = a;
+        scratch[kMaxWarps + warp_id()] = b;
+    }
+    __syncthreads();
+    double ta = (lane_id() < nw) ? scratch[lane_id()] : 0.0;
+    double tb = (lane_id() < nw) ? scratch[kMaxWarps + lane_id()] : 0.0;
+    a = warp_sum(ta);
+    b = warp_sum(tb);
+    __syncthreads();
+}
+__device__ __forceinline__ MinIdx block_argmin(MinIdx m, double* scratch_v, int* scratch_i)
+{
+    m = warp_argmin(m);
+    const int nw = (blockDim.x + 31) >> 5;
+    if (lane_id() == 0) {
+        scratch_v[warp_id()] = m.v;
+        scratch_i[warp_id()] = m.i;
+    }
+    __syncthreads();
+    MinIdx t;
+    t.v = (lane_id() < nw) ? scratch_v[lane_id()] : 0.0;
+    t.i = (lane_id() < nw) ? scratch_i[lane_id()] : -1;
+    t = warp_argmin(t);
+    __syncthreads();
+    return t;
+}
+
+} // namespace cb

@@ -1,0 +1,574 @@
+// k1_k7_lmpc.cu -- condensing (K1), QP assembly (K2-K4, K4'), result rollout (K7) for a batch of
+// LMPC / InitialStateLMPC controllers.  One CTA per instance unless noted; all instance-major,
+// reference (Eigen column-major) layouts.
+//
+// The block-Toeplitz structure of Psi (Psi_ij = A^(i-1-j) B) is exploited everywhere: only the first
+// block column Gs = [B; AB; ...; A^(N-1)B] is produced by K1, every consumer indexes it.  The
+// reference multiplies through the structural zeros (src/costFunctions.cpp:73 "Lot of sums of zero
+// here"); here Q is produced with O(N^2) block operations by running sums along block diagonals, in
+// the SAME accumulation order as the reference (steps ascending), with un-fused multiply/add so the
+// condensed matrices agree with the CPU oracle to the last bit where the order is defined.
+#include "engine.cuh"
+#include "gi_solver.cuh"
+#include "launch.h"
+
+#include <algorithm>
+#include <cfloat>
+
+namespace cb {
+
+__device__ __forceinline__ double mul_(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_(double a, double b) { return __dadd_rn(a, b); }
+
+// ------------------------------------------------------------------------------------------------
+// K1: PreviewSystem::updateSystem (reference src/PreviewSystem.cpp:57-74).
+// Phi_i = A Phi_{i-1}, G_k = A G_{k-1} (G_0 = B), xi_i = A xi_{i-1} + d.  Sequential in the step index,
+// parallel over the nx*nx + nx*nu + nx entries of one step and over instances.
+// ------------------------------------------------------------------------------------------------
+__global__ void k1_condense_kernel(const __grid_constant__ BuildParams P)
+{
+    extern __shared__ double sm[];
+    const int nx = P.nx, nu = P.nu, N = P.N, X = P.X;
+    const int nA = nx * nx, nB = nx * nu, per = nA + nB + nx;
+    double* sA = sm;            // nx x nx
+    double* cur = sA + nA;      // [Phi | G | xi] current step
+    double* nxt = cur + per;
+    double* sd = nxt + per;     // nx
+    const long long NX = (long long)N * nx;
+    for (int b = blockIdx.x; b < P.batch; b += gridDim.x) {
+        const double* A = P.A.at(b);
+        const double* Bm = P.B.at(b);
+        const double* d = P.d.at(b);
+        double* Phi = P.Phi + (long long)b * X * nx;
+        double* Gs = P.Gs + (long long)b * NX * nu;
+        double* xi = P.xi + (long long)b * X;
+        __syncthreads();
+        for (int t = threadIdx.x; t < nA; t += blockDim.x) {
+            sA[t] = A[t];
+            cur[t] = A[t]; // Phi_1 = A (assignment, :59)
+            const int r = t % nx, c = t / nx;
+            Phi[r + (long long)c * X] = (r == c) ? 1.0 : 0.0; // Phi_0 = I (PreviewSystem::system :51-52)
+            Phi[nx + r + (long long)c * X] = A[t];
+        }
+        for (int t = threadIdx.x; t < nB; t += blockDim.x) {
+            cur[nA + t] = Bm[t]; // G_0 = B (:60)
+            const int r = t % nx, c = t / nx;
+            Gs[r + (long long)c * NX] = Bm[t];
+        }
+        for (int t = threadIdx.x; t < nx; t += blockDim.x) {
+            sd[t] = d[t];
+            cur[nA + nB + t] = d[t]; // xi_1 = d (:61)
+            xi[t] = 0.0;
+            xi[nx + t] = d[t];
+        }
+        __syncthreads();
+        for (int i = 2; i <= N; ++i) {
+            for (int t = threadIdx.x; t < per; t += blockDim.x) {
+                int r, c;
+                const double* src;
+                if (t < nA) { r = t % nx; c = t / nx; src = cur + c * nx; }
+                else if (t < nA + nB) { r = (t - nA) % nx; c = (t - nA) / nx; src = cur + nA + c * nx; }
+                else { r = t - nA - nB; c = 0; src = cur + nA + nB; }
+                double s = 0.0;
+                for (int k = 0; k < nx; ++k) s = add_(s, mul_(sA[r + k * nx], src[k]));
+                if (t < nA) Phi[(long long)i * nx + r + (long long)c * X] = s;
+                else if (t < nA + nB) Gs[(long long)(i - 1) * nx + r + (long long)c * NX] = s;
+                else { s = add_(s, sd[r]); xi[(long long)i * nx + r] = s; }
+                nxt[t] = s;
+            }
+            __syncthreads();
+            double* tmp = cur; cur = nxt; nxt = tmp;
+        }
+    }
+}
+
+int k1_condense_launch(const BuildParams& P, cudaStream_t st)
+{
+    const int per = P.nx * P.nx + P.nx * P.nu + P.nx;
+    const size_t smem = sizeof(double) * size_t(P.nx * P.nx + 2 * per + P.nx);
+    int threads = std::min(256, ((per + 31) / 32) * 32);
+    int grid = std::min(P.batch, 148 * 8);
+    k1_condense_kernel<<<grid, threads, smem, st>>>(P);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 1 : -int(e);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1b: materialise Psi (X x nU, reference layout) from the compact first block column.
+// Column (j, c) of Psi is [zeros((j+1) nx); Gs[0 : X-(j+1)nx, c]]: a pure HBM-write-bound fill.
+// ------------------------------------------------------------------------------------------------
+__global__ void k1_psi_fill_kernel(const double* __restrict__ Gs, long long sGs, double* __restrict__ Psi, int nx, int nu, int N, int batch)
+{
+    const int X = nx * (N + 1), nU = nu * N;
+    const long long NX = (long long)N * nx;
+    const int b = blockIdx.y;
+    const double* g = Gs + (long long)b * sGs;
+    double* psi = Psi + (long long)b * X * nU;
+    for (int col = blockIdx.x; col < nU; col += gridDim.x) {
+        const int j = col / nu, c = col % nu;
+        const int shift = (j + 1) * nx;
+        const double* src = g + (long long)c * NX;
+        double* dst = psi + (long long)col * X;
+        for (int row = threadIdx.x; row < X; row += blockDim.x) dst[row] = (row >= shift) ? src[row - shift] : 0.0;
+    }
+}
+
+int k1_psi_fill_launch(const double* Gs, long long sGs, double* Psi, int nx, int nu, int N, int batch, cudaStream_t st)
+{
+    const int nU = nu * N;
+    int launches = 0;
+    for (int b0 = 0; b0 < batch; b0 += 65535) {
+        const int nb = std::min(65535, batch - b0);
+        dim3 grid(std::min(nU, 64), nb);
+        k1_psi_fill_kernel<<<grid, 256, 0, st>>>(Gs + (long long)b0 * sGs, sGs, Psi + (long long)b0 * nx * (N + 1) * nU, nx, nu, N, nb);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return -int(e);
+        ++launches;
+    }
+    return launches;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2a: per-family small products (one CTA per instance):
+//   cost  : MGx[kk] = M A^(kk-1) B (kk>=1), MGx[0] = N | 0 ; MPhi_i = M Phi_i ; res_i = M xi_i - p
+//   cstr  : EGx[kk] likewise with E/G ; Y rows = E Phi_i ; z rows = f - E xi_i
+// (reference: tmp = M_*Psi.block(..), M_*Phi.block(..), M_*xi.segment(..)-p_  src/costFunctions.cpp:74-78;
+//  E_*Psi.block, E_*Phi.block, f_-E_*xi.segment  src/constraints.cpp:77-81)
+// ------------------------------------------------------------------------------------------------
+__global__ void k2_precompute_kernel(const __grid_constant__ BuildParams P)
+{
+    const int nx = P.nx, nu = P.nu, N = P.N, X = P.X;
+    const long long NX = (long long)N * nx;
+    const int tid = threadIdx.x, T = blockDim.x;
+    for (int b = blockIdx.x; b < P.batch; b += gridDim.x) {
+        const double* Phi = P.Phi + (long long)b * X * nx;
+        const double* Gs = P.Gs + (long long)b * NX * nu;
+        const double* xi = P.xi + (long long)b * X;
+        for (int ci = 0; ci < P.ncost; ++ci) {
+            const CostFam& F = P.cost[ci];
+            const int r = F.rows, ns = F.i1 - F.i0;
+            const double* M = F.hasM ? F.M.at(b) : nullptr;
+            const double* Nn = F.hasN ? F.N.at(b) : nullptr;
+            const double* p = F.p.at(b);
+            double* MGx = F.MGx + (long long)b * F.sMGx;
+            double* MPhi = F.MPhi + (long long)b * F.sMPhi;
+            double* res = F.res + (long long)b * F.sres;
+            for (int t = tid; t < r * nu * (N + 1); t += T) {
+                const int l = t % r, bb = (t / r) % nu, kk = t / (r * nu);
+                double s = 0.0;
+                if (kk == 0) s = Nn ? Nn[l + bb * r] : 0.0;
+                else if (M) {
+                    const double* g = Gs + (long long)(kk - 1) * nx + (long long)bb * NX;
+                    for (int k = 0; k < nx; ++k) s = add_(s, mul_(M[l + k * r], g[k]));
+                }
+                MGx[t] = s;
+            }
+            for (int t = tid; t < r * nx * ns; t += T) {
+                const int l = t % r, sidx = (t / r) % nx, ii = t / (r * nx);
+                double s = 0.0;
+                if (M) {
+                    const double* ph = Phi + (long long)(F.i0 + ii) * nx + (long long)sidx * X;
+                    for (int k = 0; k < nx; ++k) s = add_(s, mul_(M[l + k * r], ph[k]));
+                }
+                MPhi[t] = s;
+            }
+            for (int t = tid; t < r * ns; t += T) {
+                const int l = t % r, ii = t / r;
+                double s = 0.0;
+                if (M) {
+                    const double* xv = xi + (long long)(F.i0 + ii) * nx;
+                    for (int k = 0; k < nx; ++k) s = add_(s, mul_(M[l + k * r], xv[k]));
+                    s = add_(s, -p[l]);
+                } else s = -p[l];
+                res[t] = s;
+            }
+        }
+        for (int fi = 0; fi < P.nfam; ++fi) {
+            const CstrFam& F = P.fam[fi];
+            const int r = F.rows, ns = F.i1 - F.i0;
+            const double* E = F.hasE ? F.E.at(b) : nullptr;
+            const double* G = F.hasG ? F.G.at(b) : nullptr;
+            const double* f = F.f.at(b);
+            double* EGx = F.EGx + (long long)b * F.sEGx;
+            const int mtot = F.is_eq ? P.meq : P.mineq;
+            double* Y = (F.is_eq ? P.Yeq : P.Yin) + (long long)b * mtot * nx;
+            double* z = (F.is_eq ? P.zeq : P.zin) + (long long)b * mtot;
+            for (int t = tid; t < r * nu * (N + 1); t += T) {
+                const int l = t % r, bb = (t / r) % nu, kk = t / (r * nu);
+                double s = 0.0;
+                if (kk == 0) s = G ? G[l + bb * r] : 0.0;
+                else if (E) {
+                    const double* g = Gs + (long long)(kk - 1) * nx + (long long)bb * NX;
+                    for (int k = 0; k < nx; ++k) s = add_(s, mul_(E[l + k * r], g[k]));
+                }
+                EGx[t] = s;
+            }
+            for (int t = tid; t < r * nx * ns; t += T) {
+                const int l = t % r, ii = (t / r) % ns, sidx = t / (r * ns);
+                double s = 0.0;
+                if (E) {
+                    const double* ph = Phi + (long long)(F.i0 + ii) * nx + (long long)sidx * X;
+                    for (int k = 0; k < nx; ++k) s = add_(s, mul_(E[l + k * r], ph[k]));
+                }
+                Y[(F.row_off + ii * r + l) + (long long)sidx * mtot] = s;
+            }
+            for (int t = tid; t < r * ns; t += T) {
+                const int l = t % r, ii = t / r;
+                const double fl = f[F.fidx ? F.fidx[l] : l];
+                double s = 0.0;
+                if (E) {
+                    const double* xv = xi + (long long)(F.i0 + ii) * nx;
+                    for (int k = 0; k < nx; ++k) s = add_(s, mul_(E[l + k * r], xv[k]));
+                }
+                z[F.row_off + ii * r + l] = E ? add_(fl, -s) : fl;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2b: Hessian block Q = 1e-6 I + sum_costs sum_i T_i' W T_i  (LMPC::updateSystem :228-229 +
+// makeQPForm :252-255 + cost update loops).  One thread per (block diagonal dd, a, b) chain walking
+// jmax = N-1 .. |dd|; Toeplitz => the entry at jmax is a running sum over kk = i - jmax ascending.
+// grid = (chain tiles, batch)
+// ------------------------------------------------------------------------------------------------
+__global__ void k2_assemble_q_kernel(const __grid_constant__ BuildParams P)
+{
+    const int nu = P.nu, N = P.N, nvar = P.nvar;
+    const int off = P.initial_state ? P.nx : 0;
+    const int b = blockIdx.y;
+    const int nchain = (2 * N - 1) * nu * nu;
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= nchain) return;
+    const int a = ch % nu, bb = (ch / nu) % nu, dd = ch / (nu * nu) - (N - 1); // dd = j1 - j2
+    const int ad = dd < 0 ? -dd : dd;
+    double* Q = P.Q + (long long)b * nvar * nvar;
+    double run[kMaxCost];
+    int done[kMaxCost];
+    const double* MG[kMaxCost];
+    const double* Wt[kMaxCost];
+    for (int ci = 0; ci < P.ncost; ++ci) {
+        run[ci] = 0.0;
+        done[ci] = 0;
+        MG[ci] = P.cost[ci].MGx + (long long)b * P.cost[ci].sMGx;
+        Wt[ci] = P.cost[ci].w.at(b);
+    }
+    for (int jmax = N - 1; jmax >= ad; --jmax) {
+        const int j1 = dd >= 0 ? jmax : jmax + dd;
+        const int j2 = j1 - dd;
+        double val = (dd == 0 && a == bb) ? 1e-6 : 0.0;
+        for (int ci = 0; ci < P.ncost; ++ci) {
+            const CostFam& F = P.cost[ci];
+            const int r = F.rows;
+            // steps i in [max(i0,jmax), i1-1]  <->  kk = i - jmax
+            const int kk_hi = F.i1 - 1 - jmax;
+            if (kk_hi < 0) continue;
+            double contrib;
+            if (F.i0 == 0) {
+                // running sum over kk ascending; terms are independent of jmax (Toeplitz), so only
+                // the not-yet-included kk in (done, kk_hi] are added at this jmax
+                const int o1 = jmax - j1, o2 = jmax - j2;
+                for (int kk = done[ci]; kk <= kk_hi; ++kk) {
+                    const double* ga = MG[ci] + (long long)r * (a + nu * (kk + o1));
+                    const double* gb = MG[ci] + (long long)r * (bb + nu * (kk + o2));
+                    double s = 0.0;
+                    for (int l = 0; l < r; ++l) s = add_(s, mul_(mul_(ga[l], Wt[ci][l]), gb[l]));
+                    run[ci] = add_(run[ci], s);
+                }
+                done[ci] = kk_hi + 1;
+                contrib = run[ci];
+            } else {
+                const int kk_lo = max(F.i0 - jmax, 0);
+                contrib = 0.0;
+                for (int kk = kk_lo; kk <= kk_hi; ++kk) {
+                    const double* ga = MG[ci] + (long long)r * (a + nu * (kk + jmax - j1));
+                    const double* gb = MG[ci] + (long long)r * (bb + nu * (kk + jmax - j2));
+                    double s = 0.0;
+                    for (int l = 0; l < r; ++l) s = add_(s, mul_(mul_(ga[l], Wt[ci][l]), gb[l]));
+                    contrib = add_(contrib, s);
+                }
+            }
+            val = add_(val, contrib);
+        }
+        Q[(off + j1 * nu + a) + (long long)(off + j2 * nu + bb) * nvar] = val;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2c: per-cost E (nx x nU) and f (nU):  E = sum_i MPhi_i' W T_i, f = sum_i res_i' W T_i
+// (src/costFunctions.cpp:77-78,105-106,210-211).  One thread per (s|f, column).  grid = (tiles, batch)
+// ------------------------------------------------------------------------------------------------
+__global__ void k2_assemble_ef_kernel(const __grid_constant__ BuildParams P)
+{
+    const int nx = P.nx, nu = P.nu, nU = P.nU;
+    const int b = blockIdx.y;
+    const int per = (nx + 1) * nU;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per * P.ncost) return;
+    const int ci = t / per, rem = t % per;
+    const int s = rem % (nx + 1), col = rem / (nx + 1);
+    const int j = col / nu, bb = col % nu;
+    const CostFam& F = P.cost[ci];
+    const int r = F.rows;
+    const double* MG = F.MGx + (long long)b * F.sMGx;
+    const double* MPhi = F.MPhi + (long long)b * F.sMPhi;
+    const double* res = F.res + (long long)b * F.sres;
+    const double* w = F.w.at(b);
+    double acc = 0.0;
+    for (int i = max(F.i0, j); i < F.i1; ++i) {
+        const int ii = i - F.i0;
+        const double* g = MG + (long long)r * (bb + nu * (i - j));
+        const double* lhs = (s < nx) ? MPhi + (long long)r * (s + nx * ii) : res + (long long)r * ii;
+        double sum = 0.0;
+        for (int l = 0; l < r; ++l) sum = add_(sum, mul_(mul_(lhs[l], w[l]), g[l]));
+        acc = add_(acc, sum);
+    }
+    if (s < nx) F.E[(long long)b * F.sE + s + (long long)col * nx] = acc;
+    else F.f[(long long)b * F.sf + col] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: constraint rows.  A_i[:, block j] = EGx[i-j] (j <= i, j < N), zero otherwise
+// (src/constraints.cpp:77,142,209-219,289,302); in initial-state mode the first nx columns are Y
+// (src/InitialStateLMPC.cpp:88-101).  One thread per row, coalesced down each column.
+// grid = (row tiles over meq+mineq, batch)
+// ------------------------------------------------------------------------------------------------
+__global__ void k3_fill_rows_kernel(const __grid_constant__ BuildParams P)
+{
+    const int nx = P.nx, nu = P.nu, N = P.N, nvar = P.nvar;
+    const int off = P.initial_state ? nx : 0;
+    const int b = blockIdx.y;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= P.meq + P.mineq) return;
+    const bool iseq = row < P.meq;
+    const int lrow = iseq ? row : row - P.meq;
+    const int mtot = iseq ? P.meq : P.mineq;
+    // find the family (few of them)
+    int fi = -1;
+    for (int k = 0; k < P.nfam; ++k) {
+        const CstrFam& F = P.fam[k];
+        if ((F.is_eq != 0) == iseq && lrow >= F.row_off && lrow < F.row_off + F.rows * (F.i1 - F.i0)) { fi = k; break; }
+    }
+    if (fi < 0) return;
+    const CstrFam& F = P.fam[fi];
+    const int r = F.rows;
+    const int i = F.i0 + (lrow - F.row_off) / r, l = (lrow - F.row_off) % r;
+    const double* EGx = F.EGx + (long long)b * F.sEGx;
+    double* Aout = (iseq ? P.Aeq : P.Aineq) + (long long)b * mtot * nvar;
+    if (off) {
+        const double* Y = (iseq ? P.Yeq : P.Yin) + (long long)b * mtot * nx;
+        for (int s = 0; s < nx; ++s) Aout[lrow + (long long)s * mtot] = Y[lrow + (long long)s * mtot];
+    }
+    for (int j = 0; j < N; ++j) {
+        const int kk = i - j;
+        for (int bb = 0; bb < nu; ++bb) {
+            const double v = (kk >= 0) ? EGx[l + r * (bb + nu * kk)] : 0.0;
+            Aout[lrow + (long long)(off + j * nu + bb) * mtot] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: c, beq/bineq, lb/ub (+ the E blocks of the initial-state Hessian).  One CTA per instance.
+//  LMPC : c = sum_costs (E'x0 + f) ; b = z - Y x0             (src/costFunctions.cpp:81, constraints.cpp:82, LMPC.cpp:252-279)
+//  IS   : c = [r; sum f] ; Q_tr = sum E, Q_bl = Q_tr' ; b = z  (src/InitialStateLMPC.cpp:80-121)
+// ------------------------------------------------------------------------------------------------
+__global__ void k4_finalize_kernel(const __grid_constant__ BuildParams P)
+{
+    const int nx = P.nx, nu = P.nu, nU = P.nU, nvar = P.nvar;
+    const int off = P.initial_state ? nx : 0;
+    const int tid = threadIdx.x, T = blockDim.x;
+    for (int b = blockIdx.x; b < P.batch; b += gridDim.x) {
+        const double* x0 = P.x0.at(b);
+        double* c = P.c + (long long)b * nvar;
+        double* Q = P.Q + (long long)b * nvar * nvar;
+        for (int col = tid; col < nU; col += T) {
+            double acc = 0.0;
+            for (int ci = 0; ci < P.ncost; ++ci) {
+                const CostFam& F = P.cost[ci];
+                const double* E = F.E + (long long)b * F.sE + (long long)col * nx;
+                const double fv = F.f[(long long)b * F.sf + col];
+                if (P.initial_state) acc = add_(acc, fv);
+                else {
+                    double s = 0.0;
+                    for (int a = 0; a < nx; ++a) s = add_(s, mul_(E[a], x0[a]));
+                    acc = add_(acc, add_(s, fv));
+                }
+            }
+            c[off + col] = acc;
+            if (P.initial_state) {
+                for (int a = 0; a < nx; ++a) {
+                    double e = 0.0;
+                    for (int ci = 0; ci < P.ncost; ++ci) e = add_(e, P.cost[ci].E[(long long)b * P.cost[ci].sE + a + (long long)col * nx]);
+                    Q[a + (long long)(off + col) * nvar] = e;
+                    Q[(off + col) + (long long)a * nvar] = e;
+                }
+            }
+        }
+        for (int pass = 0; pass < 2; ++pass) {
+            const int mtot = pass == 0 ? P.meq : P.mineq;
+            const double* Y = (pass == 0 ? P.Yeq : P.Yin) + (long long)b * mtot * nx;
+            const double* z = (pass == 0 ? P.zeq : P.zin) + (long long)b * mtot;
+            double* bo = (pass == 0 ? P.beq : P.bineq) + (long long)b * mtot;
+            for (int row = tid; row < mtot; row += T) {
+                if (P.initial_state) bo[row] = z[row];
+                else {
+                    double s = 0.0;
+                    for (int a = 0; a < nx; ++a) s = add_(s, mul_(Y[row + (long long)a * mtot], x0[a]));
+                    bo[row] = add_(z[row], -s);
+                }
+            }
+        }
+        double* lb = P.lb + (long long)b * nvar;
+        double* ub = P.ub + (long long)b * nvar;
+        for (int k = tid; k < nU; k += T) {
+            lb[off + k] = P.cb_lower.p ? P.cb_lower.at(b)[k % nu] : -DBL_MAX;
+            ub[off + k] = P.cb_upper.p ? P.cb_upper.at(b)[k % nu] : DBL_MAX;
+        }
+        if (P.initial_state) {
+            for (int k = tid; k < nx; k += T) {
+                c[k] = P.r.p ? P.r.at(b)[k] : 0.0;
+                lb[k] = P.x0lb.p ? P.x0lb.at(b)[k] : x0[k];
+                ub[k] = P.x0ub.p ? P.x0ub.at(b)[k] : x0[k];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4': initial-state Schur block  Q_tl = R + E Qb^-1 E'  (src/InitialStateLMPC.cpp:114-117, quirk Q7).
+// The reference inverts Qb with Eigen's LU; Qb is SPD (it contains the 1e-6 I regulariser), so the
+// GPU path uses Cholesky: Qb = U'U, J = U^-1, V = E J, Q_tl = R + V V'.  One CTA per instance; J in
+// shared memory when it fits, else in the global workspace `ws`.
+// ------------------------------------------------------------------------------------------------
+__global__ void k4_schur_kernel(const __grid_constant__ BuildParams P, double* ws, long long ws_stride, int j_smem)
+{
+    extern __shared__ double sm[];
+    const int nx = P.nx, nU = P.nU, nvar = P.nvar, ld = odd_ld(nU);
+    const int tid = threadIdx.x, T = blockDim.x;
+    double* rowbuf = sm;                 // nU + 1
+    double* V = rowbuf + nU + 1;         // nx x nU
+    double* Jm = j_smem ? V + (size_t)nx * nU : ws + (long long)blockIdx.x * ws_stride;
+    for (int b = blockIdx.x; b < P.batch; b += gridDim.x) {
+        double* Q = P.Q + (long long)b * nvar * nvar;
+        __syncthreads();
+        for (int idx = tid; idx < nU * nU; idx += T) {
+            const int i = idx % nU, j = idx / nU;
+            Jm[i + (size_t)j * ld] = Q[(nx + i) + (long long)(nx + j) * nvar];
+        }
+        __syncthreads();
+        const bool ok = chol_upper_inplace(Jm, ld, nU, rowbuf);
+        if (ok) {
+            tri_inverse_upper_inplace(Jm, ld, nU, rowbuf);
+            for (int t = tid; t < nx * nU; t += T) { // V[s,i] = sum_{k<=i} E[s,k] J[k,i]
+                const int s = t % nx, i = t / nx;
+                double acc = 0.0;
+                for (int k = 0; k <= i; ++k) acc += Q[s + (long long)(nx + k) * nvar] * Jm[k + (size_t)i * ld];
+                V[t] = acc;
+            }
+            __syncthreads();
+        }
+        for (int t = tid; t < nx * nx; t += T) {
+            const int s = t % nx, u = t / nx;
+            double acc = 0.0;
+            if (ok) for (int i = 0; i < nU; ++i) acc += V[s + (size_t)i * nx] * V[u + (size_t)i * nx];
+            else acc = CUDART_NAN; // Hessian not PD: the solver will report fail=2 on the NaN pivot
+            const double Rv = P.R.p ? P.R.at(b)[t] : 0.0;
+            Q[s + (long long)u * nvar] = Rv + acc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: LMPC::updateResults (src/LMPC.cpp:282-286 / InitialStateLMPC.cpp:124-128):
+//   control = result (tail), trajectory = Phi x0 + Psi U + xi with Psi applied as the block-Toeplitz
+//   convolution sum_{j<i} G_{i-1-j} u_j straight from the compact Gs.  One thread per trajectory row.
+// grid = (row tiles over X, batch)
+// ------------------------------------------------------------------------------------------------
+__global__ void k7_results_kernel(const __grid_constant__ BuildParams P, const double* __restrict__ xres,
+    double* __restrict__ control, double* __restrict__ traj)
+{
+    const int nx = P.nx, nu = P.nu, N = P.N, X = P.X, nU = P.nU, nvar = P.nvar;
+    const int off = P.initial_state ? nx : 0;
+    const long long NX = (long long)N * nx;
+    const int b = blockIdx.y;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const double* xr = xres + (long long)b * nvar;
+    if (control && row < nU) control[(long long)b * nU + row] = xr[off + row];
+    if (!traj || row >= X) return;
+    const double* x0 = P.initial_state ? xr : P.x0.at(b);
+    const double* Phi = P.Phi + (long long)b * X * nx;
+    const double* Gs = P.Gs + (long long)b * NX * nu;
+    const int i = row / nx, r = row % nx;
+    double s1 = 0.0;
+    for (int a = 0; a < nx; ++a) s1 = add_(s1, mul_(Phi[row + (long long)a * X], x0[a]));
+    double s2 = 0.0;
+    for (int j = 0; j < i; ++j) {
+        const double* g = Gs + (long long)(i - 1 - j) * nx + r;
+        for (int cc = 0; cc < nu; ++cc) s2 = add_(s2, mul_(g[(long long)cc * NX], xr[off + j * nu + cc]));
+    }
+    traj[(long long)b * X + row] = add_(add_(s1, s2), P.xi[(long long)b * X + row]);
+}
+
+// ------------------------------------------------------------------------------------------------
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+#define CB_CHECK_LAUNCH()                         \
+    do {                                          \
+        cudaError_t e_ = cudaGetLastError();      \
+        if (e_ != cudaSuccess) return -int(e_);   \
+        ++launches;                               \
+    } while (0)
+
+int k2k4_assemble_launch(const BuildParams& P, double* schur_ws, long long schur_stride, int sms, size_t smem_optin, cudaStream_t st)
+{
+    int launches = 0;
+    const int pgrid = std::min(P.batch, sms * 8);
+    k2_precompute_kernel<<<pgrid, 128, 0, st>>>(P);
+    CB_CHECK_LAUNCH();
+    if (P.batch > 65535) return -int(cudaErrorInvalidValue); // gridDim.y limit: the C API chunks larger batches
+    {
+        const int nb = P.batch;
+        const int nchain = (2 * P.N - 1) * P.nu * P.nu;
+        k2_assemble_q_kernel<<<dim3(ceil_div(nchain, 128), nb), 128, 0, st>>>(P);
+        CB_CHECK_LAUNCH();
+        if (P.ncost > 0) {
+            const int nef = (P.nx + 1) * P.nU * P.ncost;
+            k2_assemble_ef_kernel<<<dim3(ceil_div(nef, 128), nb), 128, 0, st>>>(P);
+            CB_CHECK_LAUNCH();
+        }
+        if (P.meq + P.mineq > 0) {
+            k3_fill_rows_kernel<<<dim3(ceil_div(P.meq + P.mineq, 128), nb), 128, 0, st>>>(P);
+            CB_CHECK_LAUNCH();
+        }
+    }
+    k4_finalize_kernel<<<pgrid, 128, 0, st>>>(P);
+    CB_CHECK_LAUNCH();
+    if (P.initial_state) {
+        const int ld = odd_ld(P.nU);
+        size_t base = sizeof(double) * (size_t(P.nU) + 1 + size_t(P.nx) * P.nU);
+        size_t withJ = base + sizeof(double) * size_t(ld) * P.nU;
+        const int j_smem = withJ + 1024 <= smem_optin ? 1 : 0;
+        const size_t smem = j_smem ? withJ : base;
+        if (!j_smem && (!schur_ws || schur_stride < (long long)ld * P.nU)) return -int(cudaErrorInvalidValue);
+        cudaError_t e = cudaFuncSetAttribute(k4_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return -int(e);
+        const int threads = P.nU <= 64 ? 64 : (P.nU <= 128 ? 128 : 256);
+        const int per_sm = int(std::max<size_t>(1, std::min<size_t>(8, smem_optin / (smem + 1024))));
+        const int grid = std::min(P.batch, sms * per_sm);
+        k4_schur_kernel<<<grid, threads, smem, st>>>(P, schur_ws, schur_stride, j_smem);
+        CB_CHECK_LAUNCH();
+    }
+    return launches;
+}
+
+int k7_results_launch(const BuildParams& P, const double* x, double* control, double* trajectory, cudaStream_t st)
+{
+    if (P.batch > 65535) return -int(cudaErrorInvalidValue);
+    const int rows = std::max(P.X, P.nU);
+    k7_results_kernel<<<dim3(ceil_div(rows, 128), P.batch), 128, 0, st>>>(P, x, control, trajectory);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 1 : -int(e);
+}
+
+} // namespace cb

@@ -1,0 +1,88 @@
+// k6_solver.cu -- batched Goldfarb-Idnani kernel (K5+K6): persistent CTAs pull instances off an
+// atomic work queue (iteration counts diverge per instance).
+#include "gi_solver.cuh"
+#include "launch.h"
+
+#include <algorithm>
+
+namespace cb {
+
+__global__ void gi_batch_kernel(const __grid_constant__ GiBatch B)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_next;
+    const GiLayout L = gi_layout(B.n, B.meq, B.m, B.j_smem, B.s_smem, B.a_smem);
+    double* gJ = B.ws ? B.ws + (long long)blockIdx.x * B.ws_stride : nullptr;
+    double* gS = gJ ? gJ + (B.j_smem ? 0 : size_t(L.ldj) * B.n) : nullptr;
+    GiWork W = gi_carve(L, smem, gJ, gS);
+    for (;;) {
+        if (threadIdx.x == 0) s_next = atomicAdd(B.counter, 1);
+        __syncthreads();
+        const int b = s_next;
+        __syncthreads();
+        if (b >= B.batch) break;
+        GiView P;
+        P.n = B.n; P.meq = B.meq; P.m = B.m;
+        P.Q = B.Q.at(b); P.c = B.c.at(b);
+        P.Aeq = B.Aeq.p ? B.Aeq.at(b) : nullptr; P.beq = B.beq.p ? B.beq.at(b) : nullptr;
+        P.Aineq = B.Aineq.p ? B.Aineq.at(b) : nullptr; P.bineq = B.bineq.p ? B.bineq.at(b) : nullptr;
+        P.lb = B.lb.at(b); P.ub = B.ub.at(b);
+        GiOut O;
+        O.x = B.x ? B.x + (long long)b * B.n : nullptr;
+        O.status = B.status ? B.status + b : nullptr;
+        O.iters = B.iters ? B.iters + 2LL * b : nullptr;
+        O.nact = B.nact ? B.nact + b : nullptr;
+        O.iact = B.iact ? B.iact + (long long)b * B.n : nullptr;
+        gi_solve(P, W, O, B.vsmall, B.max_iter);
+        __syncthreads();
+    }
+}
+
+double gi_vsmall()
+{
+    // Powell's ZQPCVX estimate as coded in qpgen2
+    double vsmall = 1.0e-60;
+    for (;;) {
+        vsmall += vsmall;
+        volatile double tmpa = 1.0 + 0.1 * vsmall;
+        volatile double tmpb = 1.0 + 0.2 * vsmall;
+        if (tmpa <= 1.0) continue;
+        if (tmpb <= 1.0) continue;
+        break;
+    }
+    return vsmall;
+}
+
+GiPlan gi_plan(int n, int meq, int m, int batch, int sms, size_t smem_optin)
+{
+    GiPlan p;
+    p.threads = n <= 64 ? 64 : (n <= 128 ? 128 : (n <= 256 ? 256 : 512));
+    const size_t budget = smem_optin > 1024 ? smem_optin - 1024 : 0; // headroom for static smem
+    const size_t small = 72 * 1024;                                  // keep >= 3 CTAs/SM when the problem is small
+    int cfg[4][3] = { { 1, 1, 1 }, { 1, 1, 0 }, { 1, 0, 0 }, { 0, 0, 0 } };
+    int pick = 3;
+    for (int k = 0; k < 4; ++k) {
+        const size_t b = gi_layout(n, meq, m, cfg[k][0], cfg[k][1], cfg[k][2]).bytes;
+        if (k == 0 && b > small) continue;
+        if (b <= budget) { pick = k; break; }
+    }
+    p.j_smem = cfg[pick][0]; p.s_smem = cfg[pick][1]; p.a_smem = cfg[pick][2];
+    const GiLayout L = gi_layout(n, meq, m, p.j_smem, p.s_smem, p.a_smem);
+    p.smem_bytes = L.bytes;
+    p.ws_stride = (p.j_smem ? 0 : (long long)L.ldj * n) + (p.s_smem ? 0 : (long long)L.lds * n);
+    int per_sm = 1;
+    if (p.smem_bytes > 0) per_sm = int(std::max<size_t>(1, std::min<size_t>(16, (smem_optin + 1024) / (p.smem_bytes + 1024))));
+    per_sm = std::min(per_sm, 2048 / p.threads);
+    p.grid = std::max(1, std::min(batch, sms * per_sm));
+    return p;
+}
+
+cudaError_t gi_launch(const GiBatch& B, const GiPlan& plan, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(gi_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes));
+    if (e != cudaSuccess) return e;
+    gi_batch_kernel<<<plan.grid, plan.threads, plan.smem_bytes, st>>>(B);
+    return cudaGetLastError();
+}
+
+} // namespace cb

@@ -1,0 +1,43 @@
+// launch.h -- host-callable launchers of the sm_100a kernels (internal to libcopra_b200.so).
+#pragma once
+#include "engine.cuh"
+#include <cuda_runtime.h>
+
+namespace cb {
+
+struct GiBatch {
+    int n, meq, m, batch;
+    DArr Q, c, Aeq, beq, Aineq, bineq, lb, ub;
+    double* x;    // n per instance (may be null)
+    int* status;  // 1
+    int* iters;   // 2
+    int* nact;    // 1
+    int* iact;    // n
+    double* ws;   // global J / S workspace, ws_stride doubles per CTA (may be null if unused)
+    long long ws_stride;
+    int* counter; // zero-initialised work-queue cursor
+    double vsmall;
+    int max_iter;
+    int j_smem, s_smem, a_smem;
+};
+
+struct GiPlan {
+    int threads, grid, j_smem, s_smem, a_smem;
+    size_t smem_bytes;
+    long long ws_stride; // doubles per CTA of global workspace
+};
+
+// choose threads / smem residency / grid for a (n, meq, m) shape on a device with `sms` SMs
+GiPlan gi_plan(int n, int meq, int m, int batch, int sms, size_t smem_optin);
+cudaError_t gi_launch(const GiBatch& B, const GiPlan& plan, cudaStream_t st);
+double gi_vsmall();
+
+// K1 .. K7 of the batched LMPC engine.  Each returns the number of kernels it launched (>0) or a
+// negative cudaError_t.
+int k1_condense_launch(const BuildParams& P, cudaStream_t st);
+int k1_psi_fill_launch(const double* Gs, long long sGs, double* Psi, int nx, int nu, int N, int batch, cudaStream_t st);
+int k2k4_assemble_launch(const BuildParams& P, double* schur_ws, long long schur_stride, int sms, size_t smem_optin,
+    cudaStream_t st);
+int k7_results_launch(const BuildParams& P, const double* x, double* control, double* trajectory, cudaStream_t st);
+
+} // namespace cb

@@ -1,0 +1,179 @@
+/*
+ * copra_b200.h -- C ABI of the B200-native batched linear-MPC engine.
+ *
+ * This is the drop-in boundary for copra's data-parallel hot path.  copra itself has
+ * no C ABI: its plug-in point is the C++ virtual class `copra::SolverInterface`
+ * (reference include/SolverInterface.h:19-81) selected through `SolverFlag` / `solverFactory`
+ * (include/solverUtils.h:34-67, src/solverUtils.cpp:9-34) and driven by `LMPC::solve`
+ * (src/LMPC.cpp:79-101).  The C++ facade in include/copra/ mirrors those classes and forwards to the
+ * entry points below; every entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C, no exceptions; return 0 = OK, < 0 = argument/CUDA error (text via
+ *     copra_b200_last_error); per-instance QP outcomes are reported in `status[]` only
+ *     (0 ok / 1 infeasible / 2 Hessian not positive definite == QuadProgDenseSolver::SI_fail,
+ *     include/QuadProgSolver.h:21-27).
+ *   - all reals are IEEE float64; matrices are column-major with ld == rows (Eigen default).
+ *   - every array argument is a (pointer, batch stride) pair; stride 0 = shared by all instances,
+ *     otherwise the distance in doubles between consecutive instances.
+ *   - `memory` says where ALL array arguments of that call live: COPRA_B200_HOST (copied over PCIe
+ *     inside the call) or COPRA_B200_DEVICE (pointers valid on the handle's device; no copies).
+ *   - a handle is bound to one CUDA device and one stream and is NOT thread-safe; multi-GPU callers
+ *     create one handle per device and shard the batch by instance index (no collective on the path).
+ *   - there is no CPU fallback: without a usable CUDA device `copra_b200_create` fails.
+ */
+#ifndef COPRA_B200_H
+#define COPRA_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COPRA_B200_ABI_VERSION 1
+
+typedef struct copra_b200_handle copra_b200_handle;
+
+enum { COPRA_B200_HOST = 0, COPRA_B200_DEVICE = 1 };
+
+/* return codes */
+enum {
+    COPRA_B200_OK = 0,
+    COPRA_B200_E_ARG = -1,     /* bad argument / dimension mismatch (std::domain_error in the facade) */
+    COPRA_B200_E_CUDA = -2,    /* CUDA runtime error */
+    COPRA_B200_E_NOGPU = -3,   /* no CUDA device: the engine has no CPU fallback */
+    COPRA_B200_E_UNSUPPORTED = -4,
+    COPRA_B200_E_STATE = -5    /* call order (e.g. download before run) */
+};
+
+typedef struct {
+    int device;          /* CUDA device ordinal */
+    void* stream;        /* cudaStream_t to launch on; NULL = the handle creates its own */
+    int sm_limit;        /* 0 = use every SM; otherwise cap the persistent grids (testing) */
+    int reserved[5];
+} copra_b200_options;
+
+typedef struct {
+    const double* ptr;
+    long long stride;    /* doubles between instances; 0 = shared */
+} copra_b200_array;
+
+/* ---- cost functions: reference include/costFunctions.h:103-219, src/costFunctions.cpp:63-215 ---- */
+enum { COPRA_B200_COST_TRAJECTORY = 0, COPRA_B200_COST_TARGET = 1, COPRA_B200_COST_CONTROL = 2, COPRA_B200_COST_MIXED = 3 };
+typedef struct {
+    int kind;
+    int rows;            /* rows of M / N / p / w (step-size entries: M rows x nx, N rows x nu) */
+    copra_b200_array M, N, p, w;
+} copra_b200_cost;
+
+/* ---- constraints: reference include/constraints.h:114-307, src/constraints.cpp:45-367 ---- */
+enum {
+    COPRA_B200_CSTR_TRAJECTORY = 0,       /* E x_i <= f (or ==), i = 0..N        */
+    COPRA_B200_CSTR_CONTROL = 1,          /* G u_i <= f (or ==), i = 0..N-1      */
+    COPRA_B200_CSTR_MIXED = 2,            /* E x_i + G u_i <= f, i = 0..N-1      */
+    COPRA_B200_CSTR_TRAJECTORY_BOUND = 3, /* lower <= x_i <= upper (+-inf lines skipped; quirk Q1) */
+    COPRA_B200_CSTR_CONTROL_BOUND = 4     /* lower <= u_i <= upper -> lb/ub      */
+};
+typedef struct {
+    int kind;
+    int rows;            /* rows of E/G/f, or entries of lower/upper */
+    int is_ineq;         /* TRAJECTORY/CONTROL/MIXED only */
+    copra_b200_array E, G, f, lower, upper;
+} copra_b200_constraint;
+
+/* ---- a batch of LMPC / InitialStateLMPC problems of ONE shape ----
+ * replaces: PreviewSystem::system (src/PreviewSystem.cpp:16-55) + LMPC::addCost/addConstraint
+ * (src/LMPC.cpp:118-128) for `batch` independent controllers. */
+typedef struct {
+    int nx, nu, N, batch;
+    int initial_state;   /* 0: copra::LMPC, 1: copra::InitialStateLMPC (decision vector [x0; U]) */
+    copra_b200_array A, B, d, x0;
+    int ncost;
+    const copra_b200_cost* costs;
+    int ncstr;
+    const copra_b200_constraint* cstrs;
+    copra_b200_array R, r, x0lb, x0ub; /* initial-state mode; ptr NULL = reference default (R=0,r=0,bounds=x0) */
+    int memory;
+} copra_b200_problem;
+
+typedef struct {
+    int X;      /* nx*(N+1) */
+    int nU;     /* nu*N     */
+    int nvar;   /* nU, or nx+nU in initial-state mode */
+    int meq, mineq;
+    int q;      /* meq + mineq + 2*nvar : QuadProg's constraint index space */
+} copra_b200_sizes;
+
+/* Outputs of a run; every pointer may be NULL.  Instance b occupies [b*len, (b+1)*len). */
+typedef struct {
+    double* control;     /* nU   per instance : LMPC::control()     (src/LMPC.cpp:284) */
+    double* trajectory;  /* X    per instance : LMPC::trajectory()  (src/LMPC.cpp:285) */
+    double* x;           /* nvar per instance : SolverInterface::SI_result()            */
+    int* status;         /* 1    per instance : SI_fail()                                */
+    int* iters;          /* 2    per instance : (outer iterations, constraint drops); [0] == SI_iter() */
+    int* nact;           /* 1    per instance : number of active constraints             */
+    int* iact;           /* nvar per instance : 1-based active indices in [eq|ineq|upper|lower] space, add order, 0 padded */
+    int memory;
+} copra_b200_results;
+
+typedef struct {
+    float h2d_ms, condense_ms, assemble_ms, solve_ms, rollout_ms, d2h_ms, total_ms;
+    long long launches;  /* kernels launched by the last call */
+} copra_b200_timing;
+
+/* identifiers for copra_b200_lmpc_download */
+enum {
+    COPRA_B200_GET_PHI = 0, COPRA_B200_GET_PSI = 1, COPRA_B200_GET_XI = 2,
+    COPRA_B200_GET_Q = 3, COPRA_B200_GET_C = 4, COPRA_B200_GET_AEQ = 5, COPRA_B200_GET_BEQ = 6,
+    COPRA_B200_GET_AINEQ = 7, COPRA_B200_GET_BINEQ = 8, COPRA_B200_GET_LB = 9, COPRA_B200_GET_UB = 10
+};
+
+/* ---------------------------------------------------------------------------------------------- */
+int copra_b200_abi_version(void);
+int copra_b200_device_count(void);
+
+int copra_b200_create(const copra_b200_options* opt, copra_b200_handle** out);
+void copra_b200_destroy(copra_b200_handle* h);
+const char* copra_b200_last_error(const copra_b200_handle* h);
+/* rebind the launch stream (e.g. to the caller framework's current stream) */
+int copra_b200_set_stream(copra_b200_handle* h, void* cuda_stream);
+int copra_b200_synchronize(copra_b200_handle* h);
+/* total kernels launched through this handle since creation */
+long long copra_b200_launch_count(const copra_b200_handle* h);
+int copra_b200_last_timing(const copra_b200_handle* h, copra_b200_timing* t);
+
+/* K1 -- replaces PreviewSystem::updateSystem (src/PreviewSystem.cpp:57-74) for a batch.
+ * Outputs (any may be NULL): Phi X x nx, Psi X x nU, xi X per instance, reference layout. */
+int copra_b200_condense(copra_b200_handle* h, int nx, int nu, int N, int batch,
+    copra_b200_array A, copra_b200_array B, copra_b200_array d,
+    double* Phi, double* Psi, double* xi, int memory);
+
+/* K5+K6 -- replaces QuadProgDenseSolver::SI_problem + SI_solve (src/QuadProgSolver.cpp:45-72) and the
+ * external Eigen::QuadProgDense::solve / qpgen2 behind it, for a batch of raw QPs
+ *   min 1/2 x'Qx + c'x   s.t.  Aeq x = beq,  Aineq x <= bineq,  lb <= x <= ub.
+ * Q n x n, Aeq meq x n, Aineq m x n (column-major).  Bounds are handled implicitly but keep
+ * QuadProg's row indices (m.. upper, m+n.. lower). */
+int copra_b200_solve_qp_batch(copra_b200_handle* h, int n, int meq, int m, int batch,
+    copra_b200_array Q, copra_b200_array c, copra_b200_array Aeq, copra_b200_array beq,
+    copra_b200_array Aineq, copra_b200_array bineq, copra_b200_array lb, copra_b200_array ub,
+    double* x, int* status, int* iters, int* nact, int* iact, int memory);
+
+/* Shape query / validation -- the dimension checks of initializeCost / initializeConstraint
+ * (src/costFunctions.cpp:44-193, src/constraints.cpp:45-357); COPRA_B200_E_ARG == std::domain_error. */
+int copra_b200_lmpc_sizes(copra_b200_handle* h, const copra_b200_problem* p, copra_b200_sizes* s);
+
+/* K1..K7 -- replaces LMPC::solve (src/LMPC.cpp:79-101) / InitialStateLMPC for `batch` controllers:
+ * updateSystem -> makeQPForm -> SI_problem -> SI_solve -> updateResults. */
+int copra_b200_lmpc_run(copra_b200_handle* h, const copra_b200_problem* p, const copra_b200_results* r);
+/* staged variants: build = K1..K5 (LMPC::updateSystem + makeQPForm), solve = K6+K7 */
+int copra_b200_lmpc_build(copra_b200_handle* h, const copra_b200_problem* p);
+int copra_b200_lmpc_solve(copra_b200_handle* h, const copra_b200_results* r);
+/* assembled stage of the last build, reference layout (LMPC::Q() c() Aeq() ... getters,
+ * include/LMPC.h:105-127); `out` must hold batch * size doubles. */
+int copra_b200_lmpc_download(copra_b200_handle* h, int what, double* out, int memory);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COPRA_B200_H */

@@ -1,0 +1,122 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+Tolerances are BASELINE.json's: condensed matrices 1e-10 relative, decision variables 1e-6,
+identical active set."""
+import numpy as np
+import pytest
+
+from copra_b200 import capi, workloads as wl
+from oracle import pyoracle as po
+from tests.util import active_set, rel_err, x_err, zeros_preserved
+
+pytestmark = pytest.mark.gpu
+
+STAGES = ("Phi", "Psi", "xi", "Q", "c", "Aeq", "beq", "Aineq", "bineq", "lb", "ub")
+
+
+def check_batch(engine, bp, instances=None, tol_mat=1e-10, tol_x=1e-6):
+    hb = capi.HostBatch(bp)
+    out = engine.lmpc_run(hb)
+    stages = {k: engine.download(hb, k) for k in STAGES}
+    idx = range(bp["batch"]) if instances is None else instances
+    worst = {}
+    for i in idx:
+        o = po.lmpc(wl.instance(bp, i))
+        for k in STAGES:
+            e = rel_err(stages[k][i], o[k])
+            worst[k] = max(worst.get(k, 0.0), e)
+            assert e <= tol_mat, (bp["name"], i, k, e)
+            assert zeros_preserved(stages[k][i], o[k]), (bp["name"], i, k, "structural zeros")
+        assert out["status"][i] == o["fail"], (bp["name"], i, out["status"][i], o["fail"])
+        if o["fail"] == 0:
+            assert x_err(out["x"][i], o["x"]) <= tol_x, (bp["name"], i, "x", x_err(out["x"][i], o["x"]))
+            assert active_set(out["iact"][i], out["nact"][i]) == active_set(o["iact"]), (bp["name"], i, "active set")
+            assert x_err(out["control"][i], o["control"]) <= tol_x
+            assert rel_err(out["trajectory"][i], o["trajectory"]) <= 1e-6
+            worst["x"] = max(worst.get("x", 0.0), x_err(out["x"][i], o["x"]))
+            worst["iter_diff"] = max(worst.get("iter_diff", 0), abs(int(out["iters"][i][0]) - o["iter"][0]))
+    print(bp["name"], {k: float("%.2e" % v) for k, v in worst.items()})
+    return worst
+
+
+def test_ka1_raw_qp(engine):
+    """reference fixture `Problem` (tests/systems.h:11-38) through the raw-QP entry (B200Solver path)"""
+    import json, os
+    ka = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ka_problem.json")))
+    r = engine.solve_qp_batch(ka["Q"], ka["c"], ka["Aeq"], ka["beq"], ka["Aineq"], ka["bineq"], ka["XL"], ka["XU"])
+    assert r["status"][0] == 0
+    assert np.abs(r["x"][0] - np.array(ka["x"])).max() < 1e-12
+    assert active_set(r["iact"][0], r["nact"][0]) == set(ka["iact"])
+    assert tuple(r["iters"][0]) == tuple(ka["iter"])
+
+
+def test_random_qps_vs_oracle(engine):
+    rng = np.random.default_rng(7)
+    drops = 0
+    for trial in range(40):
+        n = int(rng.integers(2, 25))
+        meq = int(rng.integers(0, max(1, n // 3)))
+        m = int(rng.integers(0, 2 * n))
+        B = 8
+        L = rng.normal(size=(B, n, n))
+        Q = L @ np.swapaxes(L, 1, 2) + 0.1 * np.eye(n)
+        c = rng.normal(size=(B, n))
+        Aeq = rng.normal(size=(B, meq, n))
+        xf = rng.normal(size=(B, n))  # a feasible point
+        beq = np.einsum("bij,bj->bi", Aeq, xf)
+        Aineq = rng.normal(size=(B, m, n))
+        bineq = np.einsum("bij,bj->bi", Aineq, xf) + rng.uniform(0.0, 1.0, size=(B, m))
+        lb = xf - rng.uniform(0.1, 2.0, size=(B, n))
+        ub = xf + rng.uniform(0.1, 2.0, size=(B, n))
+        lb[rng.uniform(size=(B, n)) < 0.3] = -np.inf
+        ub[rng.uniform(size=(B, n)) < 0.3] = np.finfo(float).max
+        r = engine.solve_qp_batch(Q, c, Aeq if meq else None, beq if meq else None, Aineq if m else None,
+                                  bineq if m else None, lb, ub)
+        for b in range(B):
+            o = po.quadprog(Q[b], c[b], Aeq[b], beq[b], Aineq[b], bineq[b], lb[b], ub[b])
+            assert r["status"][b] == o["fail"], (trial, b)
+            if o["fail"] == 0:
+                assert x_err(r["x"][b], o["x"]) < 1e-8, (trial, b, x_err(r["x"][b], o["x"]))
+                assert active_set(r["iact"][b], r["nact"][b]) == active_set(o["iact"]), (trial, b)
+                assert tuple(r["iters"][b]) == o["iter"], (trial, b, r["iters"][b], o["iter"])
+                drops += o["iter"][1]
+    assert drops > 0  # the drop path was exercised
+
+
+def test_infeasible_and_not_pd(engine):
+    Q = np.eye(2)
+    r = engine.solve_qp_batch(Q, np.zeros(2), None, None, np.array([[1.0, 0.0], [-1.0, 0.0]]), np.array([-1.0, -1.0]),
+                              np.full(2, -np.inf), np.full(2, np.inf))
+    assert r["status"][0] == 1  # x0 <= -1 and x0 >= 1
+    r = engine.solve_qp_batch(np.array([[1.0, 2.0], [2.0, 1.0]]), np.zeros(2), None, None, None, None,
+                              np.full(2, -1.0), np.full(2, 1.0))
+    assert r["status"][0] == 2
+
+
+@pytest.mark.parametrize("cost", ["target", "trajectory"])
+def test_c1_reference_fixture(engine, cost):
+    """configs[0]: BoundedSystem, N=300 (tests/TestLMPC.cpp:36-157) -- also checks the properties the
+    reference test asserts."""
+    bp = wl.c1(cost)
+    check_batch(engine, bp)
+    out = engine.lmpc_run(bp)
+    traj, u = out["trajectory"][0], out["control"][0]
+    assert abs(-1.0 - traj[-1]) <= 1e-3          # CHECK_LE(|xd(1) - vel.tail|, 0.001)
+    assert traj[0::2].max() <= 0.0 + 1e-12       # pos <= x0(0)
+    assert traj[1::2].max() <= 0.0 + 1e-6        # vel <= xUpper(1) + 1e-6
+    assert u.max() <= 200.0 + 1e-6               # u <= uUpper + 1e-6
+
+
+def test_c2(engine):
+    check_batch(engine, wl.c2(batch=96))
+
+
+def test_c3(engine):
+    check_batch(engine, wl.c3(batch=6))
+
+
+def test_c4_initial_state(engine):
+    check_batch(engine, wl.c4(batch=24))
+
+
+def test_c5(engine):
+    check_batch(engine, wl.c5(batch=2))
