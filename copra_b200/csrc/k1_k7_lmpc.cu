@@ -447,7 +447,8 @@ __global__ void k4_schur_kernel(const __grid_constant__ BuildParams P, double* w
     const int nx = P.nx, nU = P.nU, nvar = P.nvar, ld = odd_ld(nU);
     const int tid = threadIdx.x, T = blockDim.x;
     double* rowbuf = sm;                 // nU + 1
-    double* V = rowbuf + nU + 1;         // nx x nU
+    double* rowk = rowbuf + nU + 1;      // nU
+    double* V = rowk + nU;               // nx x nU
     double* Jm = j_smem ? V + (size_t)nx * nU : ws + (long long)blockIdx.x * ws_stride;
     for (int b = blockIdx.x; b < P.batch; b += gridDim.x) {
         double* Q = P.Q + (long long)b * nvar * nvar;
@@ -459,7 +460,7 @@ __global__ void k4_schur_kernel(const __grid_constant__ BuildParams P, double* w
         __syncthreads();
         const bool ok = chol_upper_inplace(Jm, ld, nU, rowbuf);
         if (ok) {
-            tri_inverse_upper_inplace(Jm, ld, nU, rowbuf);
+            tri_inverse_upper_inplace(Jm, ld, nU, rowbuf, rowk);
             for (int t = tid; t < nx * nU; t += T) { // V[s,i] = sum_{k<=i} E[s,k] J[k,i]
                 const int s = t % nx, i = t / nx;
                 double acc = 0.0;
@@ -546,14 +547,14 @@ int k2k4_assemble_launch(const BuildParams& P, double* schur_ws, long long schur
     CB_CHECK_LAUNCH();
     if (P.initial_state) {
         const int ld = odd_ld(P.nU);
-        size_t base = sizeof(double) * (size_t(P.nU) + 1 + size_t(P.nx) * P.nU);
+        size_t base = sizeof(double) * (2 * size_t(P.nU) + 1 + size_t(P.nx) * P.nU);
         size_t withJ = base + sizeof(double) * size_t(ld) * P.nU;
         const int j_smem = withJ + 1024 <= smem_optin ? 1 : 0;
         const size_t smem = j_smem ? withJ : base;
         if (!j_smem && (!schur_ws || schur_stride < (long long)ld * P.nU)) return -int(cudaErrorInvalidValue);
         cudaError_t e = cudaFuncSetAttribute(k4_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) return -int(e);
-        const int threads = P.nU <= 64 ? 64 : (P.nU <= 128 ? 128 : 256);
+        const int threads = P.nU <= 32 ? 128 : (P.nU <= 128 ? 256 : 512);
         const int per_sm = int(std::max<size_t>(1, std::min<size_t>(8, smem_optin / (smem + 1024))));
         const int grid = std::min(P.batch, sms * per_sm);
         k4_schur_kernel<<<grid, threads, smem, st>>>(P, schur_ws, schur_stride, j_smem);

@@ -7,11 +7,12 @@
 
 namespace cb {
 
-__global__ void gi_batch_kernel(const __grid_constant__ GiBatch B)
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) gi_batch_kernel(const __grid_constant__ GiBatch B)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_next;
-    const GiLayout L = gi_layout(B.n, B.meq, B.m, B.j_smem, B.s_smem, B.a_smem);
+    const GiLayout L = gi_layout(B.n, B.meq, B.m, blockDim.x, B.j_smem, B.s_smem, B.a_smem);
     double* gJ = B.ws ? B.ws + (long long)blockIdx.x * B.ws_stride : nullptr;
     double* gS = gJ ? gJ + (B.j_smem ? 0 : size_t(L.ldj) * B.n) : nullptr;
     GiWork W = gi_carve(L, smem, gJ, gS);
@@ -56,18 +57,19 @@ double gi_vsmall()
 GiPlan gi_plan(int n, int meq, int m, int batch, int sms, size_t smem_optin)
 {
     GiPlan p;
-    p.threads = n <= 64 ? 64 : (n <= 128 ? 128 : (n <= 256 ? 256 : 512));
+    // latency-optimised: many threads per instance (every phase is a CTA-wide GEMV / rank-1 / reduction)
+    p.threads = n <= 32 ? 128 : (n <= 128 ? 256 : 512);
     const size_t budget = smem_optin > 1024 ? smem_optin - 1024 : 0; // headroom for static smem
-    const size_t small = 72 * 1024;                                  // keep >= 3 CTAs/SM when the problem is small
+    const size_t small = 76 * 1024;                                  // keep >= 3 CTAs/SM when the problem is small
     int cfg[4][3] = { { 1, 1, 1 }, { 1, 1, 0 }, { 1, 0, 0 }, { 0, 0, 0 } };
     int pick = 3;
     for (int k = 0; k < 4; ++k) {
-        const size_t b = gi_layout(n, meq, m, cfg[k][0], cfg[k][1], cfg[k][2]).bytes;
+        const size_t b = gi_layout(n, meq, m, p.threads, cfg[k][0], cfg[k][1], cfg[k][2]).bytes;
         if (k == 0 && b > small) continue;
         if (b <= budget) { pick = k; break; }
     }
     p.j_smem = cfg[pick][0]; p.s_smem = cfg[pick][1]; p.a_smem = cfg[pick][2];
-    const GiLayout L = gi_layout(n, meq, m, p.j_smem, p.s_smem, p.a_smem);
+    const GiLayout L = gi_layout(n, meq, m, p.threads, p.j_smem, p.s_smem, p.a_smem);
     p.smem_bytes = L.bytes;
     p.ws_stride = (p.j_smem ? 0 : (long long)L.ldj * n) + (p.s_smem ? 0 : (long long)L.lds * n);
     int per_sm = 1;
@@ -77,12 +79,20 @@ GiPlan gi_plan(int n, int meq, int m, int batch, int sms, size_t smem_optin)
     return p;
 }
 
+template <int MAXT, int MINB> static cudaError_t gi_launch_t(const GiBatch& B, const GiPlan& plan, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(gi_batch_kernel<MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes));
+    if (e != cudaSuccess) return e;
+    gi_batch_kernel<MAXT, MINB><<<plan.grid, plan.threads, plan.smem_bytes, st>>>(B);
+    return cudaGetLastError();
+}
+
 cudaError_t gi_launch(const GiBatch& B, const GiPlan& plan, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(gi_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes));
-    if (e != cudaSuccess) return e;
-    gi_batch_kernel<<<plan.grid, plan.threads, plan.smem_bytes, st>>>(B);
-    return cudaGetLastError();
+    // register budgets: 128 thr x 6 CTA/SM, 256 thr x 3 CTA/SM (<= 80 regs), 512 thr x 1 (<= 128 regs)
+    if (plan.threads <= 128) return gi_launch_t<128, 6>(B, plan, st);
+    if (plan.threads <= 256) return gi_launch_t<256, 3>(B, plan, st);
+    return gi_launch_t<512, 1>(B, plan, st);
 }
 
 } // namespace cb
