@@ -7,7 +7,7 @@ OBJS := $(CSRC)/k6_solver.o $(CSRC)/k1_k7_lmpc.o $(CSRC)/capi.o
 LIB := copra_b200/lib/libcopra_b200.so
 HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/copra_b200.h
 
-all: $(LIB) oracle
+all: $(LIB) oracle tests/cpp/test_facade
 
 $(CSRC)/%.o: $(CSRC)/%.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; false)
@@ -24,3 +24,9 @@ clean:
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle clean
+
+# C++ facade tests (reference test scenarios against include/copra/*)
+tests/cpp/test_facade: tests/cpp/test_facade.cpp tests/cpp/systems.hpp $(wildcard include/copra/*) include/copra_b200.h $(LIB)
+	g++ -std=c++14 -O1 -Wall -Wextra -Iinclude -o $@ tests/cpp/test_facade.cpp -Lcopra_b200/lib -lcopra_b200 -Wl,-rpath,'$$ORIGIN/../../copra_b200/lib'
+
+facade-test: tests/cpp/test_facade

@@ -44,7 +44,7 @@ class Problem(C.Structure):
                 ("ncost", C.c_int), ("costs", C.POINTER(Cost)),
                 ("ncstr", C.c_int), ("cstrs", C.POINTER(Constraint)),
                 ("R", Array), ("r", Array), ("x0lb", Array), ("x0ub", Array),
-                ("memory", C.c_int)]
+                ("memory", C.c_int), ("flags", C.c_int)]
 
 
 class Sizes(C.Structure):
@@ -64,7 +64,8 @@ class Timing(C.Structure):
 EXPORTS = ["copra_b200_abi_version", "copra_b200_device_count", "copra_b200_create", "copra_b200_destroy",
            "copra_b200_last_error", "copra_b200_set_stream", "copra_b200_synchronize", "copra_b200_launch_count",
            "copra_b200_last_timing", "copra_b200_condense", "copra_b200_solve_qp_batch", "copra_b200_lmpc_sizes",
-           "copra_b200_lmpc_run", "copra_b200_lmpc_build", "copra_b200_lmpc_solve", "copra_b200_lmpc_download"]
+           "copra_b200_lmpc_run", "copra_b200_lmpc_build", "copra_b200_lmpc_solve", "copra_b200_lmpc_download",
+           "copra_b200_lmpc_results"]
 
 _lib = None
 
@@ -102,6 +103,7 @@ def load():
         lib.copra_b200_lmpc_build.argtypes = [C.c_void_p, C.POINTER(Problem)]
         lib.copra_b200_lmpc_solve.argtypes = [C.c_void_p, C.POINTER(Results)]
         lib.copra_b200_lmpc_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        lib.copra_b200_lmpc_results.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _lib = lib
     return _lib
 

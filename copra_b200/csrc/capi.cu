@@ -362,6 +362,7 @@ int do_build(copra_b200_handle* h, const copra_b200_problem* p)
     P.nx = nx; P.nu = nu; P.N = N; P.batch = B;
     P.X = pl.sz.X; P.nU = pl.sz.nU; P.nvar = pl.sz.nvar; P.meq = pl.sz.meq; P.mineq = pl.sz.mineq;
     P.initial_state = p->initial_state ? 1 : 0;
+    P.qdiag = (p->flags & COPRA_B200_FLAG_NO_REG) ? 0.0 : 1e-6;
     P.ncost = int(pl.costs.size());
     P.nfam = int(pl.fams.size());
 
@@ -698,6 +699,33 @@ int copra_b200_lmpc_run(copra_b200_handle* h, const copra_b200_problem* p, const
     return do_solve(h, r);
 }
 
+int copra_b200_lmpc_results(copra_b200_handle* h, const double* x, double* control, double* trajectory, int memory)
+{
+    if (!h || !x) return COPRA_B200_E_ARG;
+    if (!h->built) return fail(h, COPRA_B200_E_STATE, "results before build");
+    const BuildParams& P = h->bp;
+    const size_t B = P.batch;
+    CU(cudaSetDevice(h->device));
+    int rc;
+    const double* dx = x;
+    double *dc = control, *dt = trajectory;
+    if (memory == COPRA_B200_HOST) {
+        double* tmp = nullptr;
+        if ((rc = ws(h, "res_x", B * P.nvar, &tmp))) return rc;
+        CU(cudaMemcpyAsync(tmp, x, B * P.nvar * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        dx = tmp;
+        if ((rc = ws(h, "res_control", B * P.nU, &dc))) return rc;
+        if ((rc = ws(h, "res_traj", B * P.X, &dt))) return rc;
+    }
+    LAUNCHED(k7_results_launch(P, dx, control ? dc : nullptr, trajectory ? dt : nullptr, h->stream));
+    if (memory == COPRA_B200_HOST) {
+        if (control) CU(cudaMemcpyAsync(control, dc, B * P.nU * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (trajectory) CU(cudaMemcpyAsync(trajectory, dt, B * P.X * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
 int copra_b200_lmpc_download(copra_b200_handle* h, int what, double* out, int memory)
 {
     if (!h || !out) return COPRA_B200_E_ARG;
@@ -717,6 +745,10 @@ int copra_b200_lmpc_download(copra_b200_handle* h, int what, double* out, int me
     case COPRA_B200_GET_BINEQ: src = P.bineq; count = B * P.mineq; break;
     case COPRA_B200_GET_LB: src = P.lb; count = B * nv; break;
     case COPRA_B200_GET_UB: src = P.ub; count = B * nv; break;
+    case COPRA_B200_GET_YEQ: src = P.Yeq; count = B * P.meq * P.nx; break;
+    case COPRA_B200_GET_ZEQ: src = P.zeq; count = B * P.meq; break;
+    case COPRA_B200_GET_YINEQ: src = P.Yin; count = B * P.mineq * P.nx; break;
+    case COPRA_B200_GET_ZINEQ: src = P.zin; count = B * P.mineq; break;
     case COPRA_B200_GET_PSI: {
         count = B * size_t(P.X) * P.nU;
         double* psi = nullptr;
@@ -726,7 +758,12 @@ int copra_b200_lmpc_download(copra_b200_handle* h, int what, double* out, int me
         if (memory == COPRA_B200_DEVICE) return 0;
         src = psi;
     } break;
-    default: return fail(h, COPRA_B200_E_ARG, "unknown download id %d", what);
+    default:
+        if (what >= COPRA_B200_GET_COST_E && what < COPRA_B200_GET_COST_E + P.ncost) {
+            src = P.cost[what - COPRA_B200_GET_COST_E].E; count = B * size_t(P.nx) * P.nU;
+        } else if (what >= COPRA_B200_GET_COST_F && what < COPRA_B200_GET_COST_F + P.ncost) {
+            src = P.cost[what - COPRA_B200_GET_COST_F].f; count = B * size_t(P.nU);
+        } else return fail(h, COPRA_B200_E_ARG, "unknown download id %d", what);
     }
     if (count == 0) return 0;
     if (memory == COPRA_B200_DEVICE) CU(cudaMemcpyAsync(out, src, count * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
@@ -785,7 +822,7 @@ int copra_b200_solve_qp_batch(copra_b200_handle* h, int n, int meq, int m, int b
     if ((meq > 0 && (!Aeq.ptr || !beq.ptr)) || (m > 0 && (!Aineq.ptr || !bineq.ptr))) return fail(h, COPRA_B200_E_ARG, "constraint matrices missing");
     CU(cudaSetDevice(h->device));
     h->call_launches = 0;
-    h->built = false;
+    /* the last lmpc build stays valid: this entry uses its own workspace buffers */
     for (bool& v : h->ev_valid) v = false;
     int rc = record(h, 0);
     if (rc) return rc;

@@ -29,16 +29,20 @@ __device__ __forceinline__ MinIdx better(MinIdx a, MinIdx b)
     if (b.i >= 0 && (a.i < 0 || b.v < a.v || (b.v == a.v && b.i < a.i))) return b;
     return a;
 }
+// Warp arg-min: minimum value by a butterfly of fmin, then the lowest index among the lanes that hold
+// it through the redux unit (one instruction) -- same result as the pairwise `better` tournament.
 __device__ __forceinline__ MinIdx warp_argmin(MinIdx m)
 {
+    const bool has = m.i >= 0;
+    double v = has ? m.v : CUDART_INF;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        MinIdx t;
-        t.v = __shfl_xor_sync(0xffffffffu, m.v, o);
-        t.i = __shfl_xor_sync(0xffffffffu, m.i, o);
-        m = better(m, t);
-    }
-    return m;
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const unsigned idx = __reduce_min_sync(0xffffffffu, (has && m.v == v) ? unsigned(m.i) : 0xffffffffu);
+    MinIdx r;
+    r.v = v;
+    r.i = (idx == 0xffffffffu) ? -1 : int(idx);
+    if (r.i < 0) r.v = 0.0;
+    return r;
 }
 
 // Block-wide reductions through a small smem scratch (>= kMaxWarps entries each).  All threads

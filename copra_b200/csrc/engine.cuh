@@ -57,6 +57,7 @@ struct BuildParams {
     int X, nU, nvar, meq, mineq;
     int initial_state;
     int ncost, nfam;
+    double qdiag;                 // 1e-6 (LMPC::updateSystem) or 0
     DArr A, B, d, x0;
     DArr R, r, x0lb, x0ub;        // initial-state mode (p may be null)
     DArr cb_lower, cb_upper;      // ControlBoundConstraint (p null = none)

@@ -256,7 +256,7 @@ __global__ void k2_assemble_q_kernel(const __grid_constant__ BuildParams P)
     for (int jmax = N - 1; jmax >= ad; --jmax) {
         const int j1 = dd >= 0 ? jmax : jmax + dd;
         const int j2 = j1 - dd;
-        double val = (dd == 0 && a == bb) ? 1e-6 : 0.0;
+        double val = (dd == 0 && a == bb) ? P.qdiag : 0.0;
         for (int ci = 0; ci < P.ncost; ++ci) {
             const CostFam& F = P.cost[ci];
             const int r = F.rows;

@@ -1,6 +1,7 @@
 // k6_solver.cu -- batched Goldfarb-Idnani kernel (K5+K6): persistent CTAs pull instances off an
 // atomic work queue (iteration counts diverge per instance).
 #include "gi_solver.cuh"
+#include "gi_small.cuh"
 #include "launch.h"
 
 #include <algorithm>
@@ -39,6 +40,36 @@ __global__ void __launch_bounds__(MAXT, MINB) gi_batch_kernel(const __grid_const
     }
 }
 
+// n <= 64: latency-optimised 128-thread variant (gi_small.cuh), everything resident in shared memory
+__global__ void __launch_bounds__(kSmT, 3) gi_small_kernel(const __grid_constant__ GiBatch B)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_next;
+    const GsLayout L = gs_layout(B.n, B.meq, B.m);
+    GsWork W = gs_carve(L, smem);
+    for (;;) {
+        if (threadIdx.x == 0) s_next = atomicAdd(B.counter, 1);
+        __syncthreads();
+        const int b = s_next;
+        __syncthreads();
+        if (b >= B.batch) break;
+        GiView P;
+        P.n = B.n; P.meq = B.meq; P.m = B.m;
+        P.Q = B.Q.at(b); P.c = B.c.at(b);
+        P.Aeq = B.Aeq.p ? B.Aeq.at(b) : nullptr; P.beq = B.beq.p ? B.beq.at(b) : nullptr;
+        P.Aineq = B.Aineq.p ? B.Aineq.at(b) : nullptr; P.bineq = B.bineq.p ? B.bineq.at(b) : nullptr;
+        P.lb = B.lb.at(b); P.ub = B.ub.at(b);
+        GiOut O;
+        O.x = B.x ? B.x + (long long)b * B.n : nullptr;
+        O.status = B.status ? B.status + b : nullptr;
+        O.iters = B.iters ? B.iters + 2LL * b : nullptr;
+        O.nact = B.nact ? B.nact + b : nullptr;
+        O.iact = B.iact ? B.iact + (long long)b * B.n : nullptr;
+        gs_solve(P, L, W, O, B.vsmall, B.max_iter);
+        __syncthreads();
+    }
+}
+
 double gi_vsmall()
 {
     // Powell's ZQPCVX estimate as coded in qpgen2
@@ -57,7 +88,21 @@ double gi_vsmall()
 GiPlan gi_plan(int n, int meq, int m, int batch, int sms, size_t smem_optin)
 {
     GiPlan p;
-    // latency-optimised: many threads per instance (every phase is a CTA-wide GEMV / rank-1 / reduction)
+    p.small = 0;
+    if (n <= kSmMaxN) {
+        const size_t b = gs_layout(n, meq, m).bytes;
+        if (b + 2048 <= smem_optin) {
+            p.small = 1;
+            p.threads = kSmT;
+            p.j_smem = p.s_smem = p.a_smem = 1;
+            p.smem_bytes = b;
+            p.ws_stride = 0;
+            const int per_sm = int(std::max<size_t>(1, std::min<size_t>(12, (smem_optin + 1024) / (b + 1024))));
+            p.grid = std::max(1, std::min(batch, sms * per_sm));
+            return p;
+        }
+    }
+    // general path: many threads per instance (every phase is a CTA-wide GEMV / rank-1 / reduction)
     p.threads = n <= 32 ? 128 : (n <= 128 ? 256 : 512);
     const size_t budget = smem_optin > 1024 ? smem_optin - 1024 : 0; // headroom for static smem
     const size_t small = 76 * 1024;                                  // keep >= 3 CTAs/SM when the problem is small
@@ -89,6 +134,12 @@ template <int MAXT, int MINB> static cudaError_t gi_launch_t(const GiBatch& B, c
 
 cudaError_t gi_launch(const GiBatch& B, const GiPlan& plan, cudaStream_t st)
 {
+    if (plan.small) {
+        cudaError_t e = cudaFuncSetAttribute(gi_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes));
+        if (e != cudaSuccess) return e;
+        gi_small_kernel<<<plan.grid, plan.threads, plan.smem_bytes, st>>>(B);
+        return cudaGetLastError();
+    }
     // register budgets: 128 thr x 6 CTA/SM, 256 thr x 3 CTA/SM (<= 80 regs), 512 thr x 1 (<= 128 regs)
     if (plan.threads <= 128) return gi_launch_t<128, 6>(B, plan, st);
     if (plan.threads <= 256) return gi_launch_t<256, 3>(B, plan, st);

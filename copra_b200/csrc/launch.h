@@ -23,6 +23,7 @@ struct GiBatch {
 
 struct GiPlan {
     int threads, grid, j_smem, s_smem, a_smem;
+    int small; // 1: gi_small_kernel (n <= 64, all state in shared memory)
     size_t smem_bytes;
     long long ws_stride; // doubles per CTA of global workspace
 };

@@ -1,0 +1,3 @@
+// Drop-in include name of the reference (copra/constraints.h); the implementation lives in copra_b200_facade.hpp.
+#pragma once
+#include "copra_b200_facade.hpp"

@@ -95,7 +95,12 @@ typedef struct {
     const copra_b200_constraint* cstrs;
     copra_b200_array R, r, x0lb, x0ub; /* initial-state mode; ptr NULL = reference default (R=0,r=0,bounds=x0) */
     int memory;
+    int flags;           /* COPRA_B200_FLAG_* */
 } copra_b200_problem;
+
+/* LMPC::updateSystem starts every Hessian at 1e-6*I (src/LMPC.cpp:228-229).  The facade sets NO_REG when it
+ * evaluates ONE cost function in isolation (CostFunction::Q() getter), where the reference has no such term. */
+#define COPRA_B200_FLAG_NO_REG 1
 
 typedef struct {
     int X;      /* nx*(N+1) */
@@ -126,7 +131,11 @@ typedef struct {
 enum {
     COPRA_B200_GET_PHI = 0, COPRA_B200_GET_PSI = 1, COPRA_B200_GET_XI = 2,
     COPRA_B200_GET_Q = 3, COPRA_B200_GET_C = 4, COPRA_B200_GET_AEQ = 5, COPRA_B200_GET_BEQ = 6,
-    COPRA_B200_GET_AINEQ = 7, COPRA_B200_GET_BINEQ = 8, COPRA_B200_GET_LB = 9, COPRA_B200_GET_UB = 10
+    COPRA_B200_GET_AINEQ = 7, COPRA_B200_GET_BINEQ = 8, COPRA_B200_GET_LB = 9, COPRA_B200_GET_UB = 10,
+    COPRA_B200_GET_YEQ = 11, COPRA_B200_GET_ZEQ = 12, COPRA_B200_GET_YINEQ = 13, COPRA_B200_GET_ZINEQ = 14,
+    /* per-cost E() (nx x nU) and f() (nU) of cost i: COPRA_B200_GET_COST_E + i, COPRA_B200_GET_COST_F + i
+     * (CostFunction::E() / f(), include/costFunctions.h:85-87) */
+    COPRA_B200_GET_COST_E = 100, COPRA_B200_GET_COST_F = 200
 };
 
 /* ---------------------------------------------------------------------------------------------- */
@@ -169,6 +178,9 @@ int copra_b200_lmpc_run(copra_b200_handle* h, const copra_b200_problem* p, const
 /* staged variants: build = K1..K5 (LMPC::updateSystem + makeQPForm), solve = K6+K7 */
 int copra_b200_lmpc_build(copra_b200_handle* h, const copra_b200_problem* p);
 int copra_b200_lmpc_solve(copra_b200_handle* h, const copra_b200_results* r);
+/* K7 alone -- LMPC::updateResults (src/LMPC.cpp:282-286) for an externally solved QP: `x` holds nvar doubles per
+ * instance (the SI_result() of any SolverInterface); control / trajectory as in copra_b200_results. */
+int copra_b200_lmpc_results(copra_b200_handle* h, const double* x, double* control, double* trajectory, int memory);
 /* assembled stage of the last build, reference layout (LMPC::Q() c() Aeq() ... getters,
  * include/LMPC.h:105-127); `out` must hold batch * size doubles. */
 int copra_b200_lmpc_download(copra_b200_handle* h, int what, double* out, int memory);
