@@ -58,6 +58,18 @@ def k6_algorithmic_bytes(sz):
     return 8 * (n * n + n + (meq + m) * n + (meq + m) + 2 * n) + 8 * n + 4 * q + 12
 
 
+def k6_algorithmic_flops(sz, iters):
+    """F_alg = 2/3 n^3 + I (10 n^2 + 2 n q), I = outer iterations"""
+    n, q = sz["nvar"], sz["q"]
+    return (2.0 / 3.0) * n ** 3 + iters * (10.0 * n * n + 2.0 * n * q)
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the K6 kernel from the committed
+# `ncu --set full` capture (profiles/r01_gi_small_c2_ncu_raw.txt); only valid for that exact workload
+NCU_TRAFFIC = {("c2", 4096): 172143616 + 4955136}
+FP64_PEAK_TFLOPS = 37.0  # nominal B200 FP64 (vector == tensor); not in MEASURED_PEAKS.json
+
+
 class ClockSampler:
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -73,7 +85,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=open(self.path, "w"),
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=open(self.path, "w"),
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -246,14 +258,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- warm-up -------------------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()  # samples clocks / throttle reasons through warm-up, the timed region and the e2e loop
     for _ in range(args.warmup):
         step_device()
     torch.cuda.synchronize()
     n_ok = int((d_status == 0).sum().item())
 
     # ---- value: device-resident inputs, CUDA events per step, L2 flushed between steps ----------
-    sampler = ClockSampler(local)
-    sampler.start()
     l0 = eng.launch_count()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -275,7 +287,6 @@ def main():
     tm = eng.timing()
     for k in stage:
         stage[k] = tm[k]
-    clocks = sampler.stop()
 
     total_ms = sum(step_ms)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -299,6 +310,7 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * batch * e2e_steps / float(te.item())
     ok_host = int((h_status == 0).sum().item())
+    clocks = sampler.stop()
 
     # ---- final gather of per-rank results (status counts, timings): the only cross-GPU traffic ---
     summary = torch.tensor([float(n_ok), float(ok_host), total_ms, float(launches)], dtype=torch.float64, device=dev)
@@ -312,6 +324,8 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         k6_bytes = k6_algorithmic_bytes(sz) * batch
+        mean_iters = float(d_iters.view(-1, 2)[:, 0].double().mean().item())
+        k6_flops = k6_algorithmic_flops(sz, mean_iters) * batch
         solve_s = stage["solve_ms"] * 1e-3
         achieved = k6_bytes / solve_s / 1e9 if solve_s > 0 else 0.0
         step_total = stage["condense_ms"] + stage["assemble_ms"] + stage["solve_ms"] + stage["rollout_ms"]
@@ -327,7 +341,10 @@ def main():
             solved_ok=int(summary_all[:, 0].sum()), instances=world * batch,
             stage_ms=stage,
             roofline=dict(kernel="gi_batch_kernel (K5+K6)", bound="hbm", achieved=achieved, peak=peak, unit="GB/s",
-                          frac=achieved / peak, traffic=None, peak_source=peak_src,
+                          frac=achieved / peak, traffic=NCU_TRAFFIC.get((config, batch)), peak_source=peak_src,
+                          fp64=dict(achieved_tflops=(k6_flops / solve_s / 1e12) if solve_s > 0 else 0.0, nominal_peak_tflops=FP64_PEAK_TFLOPS,
+                                    frac=(k6_flops / solve_s / 1e12 / FP64_PEAK_TFLOPS) if solve_s > 0 else 0.0, mean_outer_iterations=mean_iters,
+                                    note="algorithmic flops 2/3 n^3 + I(10 n^2 + 2 n q) vs NOMINAL FP64 peak (no measured FP64 peak on this pool)"),
                           share_of_step=(stage["solve_ms"] / step_total) if step_total > 0 else None,
                           note="K6 is FP64-latency bound by arithmetic intensity; HBM fraction reported as north_star asks"),
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=hb_host.h2d_bytes, d2h_bytes_per_step=d2h_bytes,

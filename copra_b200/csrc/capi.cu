@@ -6,6 +6,7 @@
 #include "../../include/copra_b200.h"
 #include "engine.cuh"
 #include "launch.h"
+#include "gi_solver.cuh"
 
 #include <cfloat>
 #include <cmath>
@@ -344,6 +345,49 @@ template <class T> int ws(copra_b200_handle* h, const char* name, size_t count, 
     return rc;
 }
 
+// Launch K5+K6 for a prepared batch: picks the small / single-CTA / cluster variant and provides the
+// workspace each needs.  Returns 0 or a negative C-ABI code; counts the kernels it launched.
+int run_gi(copra_b200_handle* h, GiBatch& G)
+{
+    int rc;
+    const int sms = h->sm_limit > 0 ? std::min(h->sm_limit, h->sms) : h->sms;
+    GiPlan plan = gi_plan(G.n, G.meq, G.m, G.batch, sms, h->smem_optin);
+    int* counter = nullptr;
+    if ((rc = ws(h, "counter", 2, &counter))) return rc;
+    CU(cudaMemsetAsync(counter, 0, 2 * sizeof(int), h->stream));
+    G.counter = counter;
+    G.vsmall = h->vsmall;
+    G.max_iter = 50 * (G.meq + G.m + 2 * G.n) + 100;
+    G.j_smem = plan.j_smem; G.s_smem = plan.s_smem; G.a_smem = plan.a_smem;
+    G.ws = nullptr; G.ws_stride = plan.ws_stride;
+    if (plan.cluster > 0) {
+        int nclusters = gi_cluster_max_clusters(plan);
+        if (nclusters > 0) {
+            nclusters = std::min(nclusters, G.batch);
+            const size_t n = G.n;
+            double* Sws = nullptr;
+            if ((rc = ws(h, "gi_S", size_t(nclusters) * odd_ld(G.n) * n, &Sws))) return rc;
+            cudaError_t e = gi_cluster_launch(G, plan, Sws, nclusters, h->stream);
+            if (e != cudaSuccess) return fail(h, COPRA_B200_E_CUDA, "gi_cluster_launch: %s", cudaGetErrorString(e));
+            h->launches += 1; h->call_launches += 1;
+            return 0;
+        }
+        // clusters of this size cannot be scheduled on this device: fall back to the single-CTA variant
+        plan.cluster = 0;
+        plan.threads = 512; plan.j_smem = plan.s_smem = plan.a_smem = 0;
+        plan.smem_bytes = gi_layout(G.n, G.meq, G.m, 512, 0, 0, 0).bytes;
+        plan.ws_stride = 2LL * odd_ld(G.n) * G.n;
+        plan.grid = std::max(1, std::min(G.batch, sms));
+        G.j_smem = G.s_smem = G.a_smem = 0;
+        G.ws_stride = plan.ws_stride;
+    }
+    if (plan.ws_stride > 0 && (rc = ws(h, "gi_ws", size_t(plan.grid) * plan.ws_stride, &G.ws))) return rc;
+    cudaError_t e = gi_launch(G, plan, h->stream);
+    if (e != cudaSuccess) return fail(h, COPRA_B200_E_CUDA, "gi_launch: %s", cudaGetErrorString(e));
+    h->launches += 1; h->call_launches += 1;
+    return 0;
+}
+
 int do_build(copra_b200_handle* h, const copra_b200_problem* p)
 {
     Plan pl;
@@ -514,7 +558,7 @@ int do_solve(copra_b200_handle* h, const copra_b200_results* r)
     const size_t B = P.batch, nv = P.nvar;
     int rc;
     double *x = nullptr, *control = nullptr, *traj = nullptr;
-    int *status = nullptr, *iters = nullptr, *nact = nullptr, *iact = nullptr, *counter = nullptr;
+    int *status = nullptr, *iters = nullptr, *nact = nullptr, *iact = nullptr;
     const bool devres = r && r->memory == COPRA_B200_DEVICE;
     if ((rc = ws(h, "res_x", B * nv, &x))) return rc;
     if ((rc = ws(h, "res_control", B * P.nU, &control))) return rc;
@@ -523,7 +567,6 @@ int do_solve(copra_b200_handle* h, const copra_b200_results* r)
     if ((rc = ws(h, "res_iters", 2 * B, &iters))) return rc;
     if ((rc = ws(h, "res_nact", B, &nact))) return rc;
     if ((rc = ws(h, "res_iact", B * nv, &iact))) return rc;
-    if ((rc = ws(h, "counter", 1, &counter))) return rc;
     if (devres) { // write straight into the caller's device buffers where given
         if (r->x) x = r->x;
         if (r->control) control = r->control;
@@ -533,8 +576,6 @@ int do_solve(copra_b200_handle* h, const copra_b200_results* r)
         if (r->nact) nact = r->nact;
         if (r->iact) iact = r->iact;
     }
-    const int sms = h->sm_limit > 0 ? std::min(h->sm_limit, h->sms) : h->sms;
-    GiPlan plan = gi_plan(P.nvar, P.meq, P.mineq, P.batch, sms, h->smem_optin);
     GiBatch G{};
     G.n = P.nvar; G.meq = P.meq; G.m = P.mineq; G.batch = P.batch;
     G.Q = DArr{ P.Q, (long long)(nv * nv) };
@@ -546,16 +587,7 @@ int do_solve(copra_b200_handle* h, const copra_b200_results* r)
     G.lb = DArr{ P.lb, (long long)nv };
     G.ub = DArr{ P.ub, (long long)nv };
     G.x = x; G.status = status; G.iters = iters; G.nact = nact; G.iact = iact;
-    G.counter = counter;
-    G.vsmall = h->vsmall;
-    G.max_iter = 50 * (P.meq + P.mineq + 2 * P.nvar) + 100;
-    G.j_smem = plan.j_smem; G.s_smem = plan.s_smem; G.a_smem = plan.a_smem;
-    G.ws = nullptr; G.ws_stride = plan.ws_stride;
-    if (plan.ws_stride > 0 && (rc = ws(h, "gi_ws", size_t(plan.grid) * plan.ws_stride, &G.ws))) return rc;
-    CU(cudaMemsetAsync(counter, 0, sizeof(int), h->stream));
-    cudaError_t e = gi_launch(G, plan, h->stream);
-    if (e != cudaSuccess) return fail(h, COPRA_B200_E_CUDA, "gi_launch: %s", cudaGetErrorString(e));
-    h->launches += 1; h->call_launches += 1;
+    if ((rc = run_gi(h, G))) return rc;
     if ((rc = record(h, 4))) return rc;
     const bool want_ct = !r || r->control || r->trajectory;
     if (want_ct) LAUNCHED(k7_results_launch(P, x, control, traj, h->stream));
@@ -840,26 +872,13 @@ int copra_b200_solve_qp_batch(copra_b200_handle* h, int n, int meq, int m, int b
     h->ev_valid[2] = h->ev_valid[3] = false;
     const size_t B = batch;
     const bool dv = memory == COPRA_B200_DEVICE;
-    int* counter = nullptr;
     if (dv && x) G.x = x; else if ((rc = ws(h, "res_x", B * n, &G.x))) return rc;
     if (dv && status) G.status = status; else if ((rc = ws(h, "res_status", B, &G.status))) return rc;
     if (dv && iters) G.iters = iters; else if ((rc = ws(h, "res_iters", 2 * B, &G.iters))) return rc;
     if (dv && nact) G.nact = nact; else if ((rc = ws(h, "res_nact", B, &G.nact))) return rc;
     if (dv && iact) G.iact = iact; else if ((rc = ws(h, "res_iact", B * n, &G.iact))) return rc;
-    if ((rc = ws(h, "counter", 1, &counter))) return rc;
-    const int sms = h->sm_limit > 0 ? std::min(h->sm_limit, h->sms) : h->sms;
-    GiPlan plan = gi_plan(n, meq, m, batch, sms, h->smem_optin);
-    G.counter = counter;
-    G.vsmall = h->vsmall;
-    G.max_iter = 50 * (meq + m + 2 * n) + 100;
-    G.j_smem = plan.j_smem; G.s_smem = plan.s_smem; G.a_smem = plan.a_smem;
-    G.ws_stride = plan.ws_stride;
-    if (plan.ws_stride > 0 && (rc = ws(h, "gi_ws", size_t(plan.grid) * plan.ws_stride, &G.ws))) return rc;
-    CU(cudaMemsetAsync(counter, 0, sizeof(int), h->stream));
     if ((rc = record(h, 3))) return rc;
-    cudaError_t e = gi_launch(G, plan, h->stream);
-    if (e != cudaSuccess) return fail(h, COPRA_B200_E_CUDA, "gi_launch: %s", cudaGetErrorString(e));
-    h->launches += 1; h->call_launches += 1;
+    if ((rc = run_gi(h, G))) return rc;
     if ((rc = record(h, 4))) return rc;
     if ((rc = record(h, 5))) return rc;
     if (!dv) {

@@ -127,7 +127,7 @@ __device__ inline GiWork gi_carve(const GiLayout& L, unsigned char* smem, double
 template <class F> __device__ __forceinline__ void tile_rc(int rows, int c0, int c1, F f)
 {
     const int tid = threadIdx.x, T = blockDim.x;
-    const int rp = round32(rows);
+    const int rp = max(32, round32(rows));
     if (T >= rp) {
         const int G = T / rp, g = tid / rp, r = tid - g * rp;
         if (g < G && r < rows)
@@ -145,7 +145,7 @@ __device__ __forceinline__ void row_dots(const double* __restrict__ M, int ld, i
     const double* __restrict__ vec, double* __restrict__ out, double* __restrict__ part)
 {
     const int tid = threadIdx.x, T = blockDim.x;
-    const int rp = round32(rows);
+    const int rp = max(32, round32(rows));
     const int G = T / rp;
     if (G <= 1) {
         for (int r = tid; r < rows; r += T) {

@@ -2,9 +2,11 @@
 // atomic work queue (iteration counts diverge per instance).
 #include "gi_solver.cuh"
 #include "gi_small.cuh"
+#include "gi_cluster.cuh"
 #include "launch.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace cb {
 
@@ -70,6 +72,42 @@ __global__ void __launch_bounds__(kSmT, 3) gi_small_kernel(const __grid_constant
     }
 }
 
+// ---- large n: one thread-block cluster per instance (gi_cluster.cuh) -----------------------------------
+__global__ void __launch_bounds__(512, 1) gi_cluster_kernel(const __grid_constant__ GiBatch B, double* __restrict__ Sws, int C)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = int(cluster.block_rank());
+    const int cid = blockIdx.x / C; // cluster index
+    const GcLayout L = gc_layout(B.n, B.meq, B.m, C, blockDim.x);
+    GcWork W = gc_carve(L, smem);
+    const int lds = odd_ld(B.n);
+    double* S = Sws + (long long)cid * lds * B.n;
+    for (;;) {
+        cluster.sync(); // every CTA is done with the previous instance (DSMEM buffers are free)
+        if (rank == 0 && threadIdx.x == 0) {
+            const int nb = atomicAdd(B.counter, 1);
+            for (int t = 0; t < C; ++t) cluster.map_shared_rank(W.ctl, t)[0] = nb;
+        }
+        cluster.sync();
+        const int b = W.ctl[0];
+        if (b >= B.batch) break;
+        GiOut O;
+        O.x = B.x ? B.x + (long long)b * B.n : nullptr;
+        O.status = B.status ? B.status + b : nullptr;
+        O.iters = B.iters ? B.iters + 2LL * b : nullptr;
+        O.nact = B.nact ? B.nact + b : nullptr;
+        O.iact = B.iact ? B.iact + (long long)b * B.n : nullptr;
+        GiView P;
+        P.n = B.n; P.meq = B.meq; P.m = B.m;
+        P.Q = B.Q.at(b); P.c = B.c.at(b);
+        P.Aeq = B.Aeq.p ? B.Aeq.at(b) : nullptr; P.beq = B.beq.p ? B.beq.at(b) : nullptr;
+        P.Aineq = B.Aineq.p ? B.Aineq.at(b) : nullptr; P.bineq = B.bineq.p ? B.bineq.at(b) : nullptr;
+        P.lb = B.lb.at(b); P.ub = B.ub.at(b);
+        gc_solve(P, L, W, S, lds, O, B.vsmall, B.max_iter);
+    }
+}
+
 double gi_vsmall()
 {
     // Powell's ZQPCVX estimate as coded in qpgen2
@@ -85,10 +123,18 @@ double gi_vsmall()
     return vsmall;
 }
 
+static int gi_cluster_threads()
+{
+    const char* e = getenv("COPRA_B200_CLUSTER_THREADS"); // tuning knob
+    const int t = e ? atoi(e) : 512;
+    return (t == 128 || t == 256 || t == 512) ? t : 512;
+}
+
 GiPlan gi_plan(int n, int meq, int m, int batch, int sms, size_t smem_optin)
 {
     GiPlan p;
     p.small = 0;
+    p.cluster = 0;
     if (n <= kSmMaxN) {
         const size_t b = gs_layout(n, meq, m).bytes;
         if (b + 2048 <= smem_optin) {
@@ -100,6 +146,22 @@ GiPlan gi_plan(int n, int meq, int m, int batch, int sms, size_t smem_optin)
             const int per_sm = int(std::max<size_t>(1, std::min<size_t>(12, (smem_optin + 1024) / (b + 1024))));
             p.grid = std::max(1, std::min(batch, sms * per_sm));
             return p;
+        }
+    }
+    // n too large for one SM's shared memory: a cluster of C CTAs shares J through DSMEM
+    if (size_t(odd_ld(n)) * n * sizeof(double) + 24 * 1024 > smem_optin) {
+        for (int C = 2; C <= kClMaxC; C *= 2) {
+            const int cth = gi_cluster_threads();
+            const size_t b = gc_layout(n, meq, m, C, cth).bytes;
+            if (b + 2048 <= smem_optin) {
+                p.cluster = C;
+                p.threads = cth;
+                p.smem_bytes = b;
+                p.j_smem = 1; p.s_smem = 0; p.a_smem = 0;
+                p.ws_stride = 0;
+                p.grid = 0; // sized at launch from cudaOccupancyMaxActiveClusters
+                return p;
+            }
         }
     }
     // general path: many threads per instance (every phase is a CTA-wide GEMV / rank-1 / reduction)
@@ -130,6 +192,47 @@ template <int MAXT, int MINB> static cudaError_t gi_launch_t(const GiBatch& B, c
     if (e != cudaSuccess) return e;
     gi_batch_kernel<MAXT, MINB><<<plan.grid, plan.threads, plan.smem_bytes, st>>>(B);
     return cudaGetLastError();
+}
+
+cudaError_t gi_cluster_launch(const GiBatch& B, const GiPlan& plan, double* Sws, int nclusters, cudaStream_t st)
+{
+    cudaError_t e;
+    // cluster solve
+    e = cudaFuncSetAttribute(gi_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes));
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(nclusters * plan.cluster));
+    cfg.blockDim = dim3(unsigned(plan.threads));
+    cfg.dynamicSmemBytes = plan.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = unsigned(plan.cluster);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int C = plan.cluster;
+    return cudaLaunchKernelEx(&cfg, gi_cluster_kernel, B, Sws, C);
+}
+
+int gi_cluster_max_clusters(const GiPlan& plan)
+{
+    if (cudaFuncSetAttribute(gi_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes)) != cudaSuccess) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(plan.cluster * 64));
+    cfg.blockDim = dim3(unsigned(plan.threads));
+    cfg.dynamicSmemBytes = plan.smem_bytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = unsigned(plan.cluster);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, gi_cluster_kernel, &cfg) != cudaSuccess) return 0;
+    return nc;
 }
 
 cudaError_t gi_launch(const GiBatch& B, const GiPlan& plan, cudaStream_t st)

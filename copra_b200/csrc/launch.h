@@ -24,6 +24,7 @@ struct GiBatch {
 struct GiPlan {
     int threads, grid, j_smem, s_smem, a_smem;
     int small; // 1: gi_small_kernel (n <= 64, all state in shared memory)
+    int cluster; // > 0: gi_cluster_kernel with this cluster size (J distributed over DSMEM)
     size_t smem_bytes;
     long long ws_stride; // doubles per CTA of global workspace
 };
@@ -32,6 +33,9 @@ struct GiPlan {
 GiPlan gi_plan(int n, int meq, int m, int batch, int sms, size_t smem_optin);
 cudaError_t gi_launch(const GiBatch& B, const GiPlan& plan, cudaStream_t st);
 double gi_vsmall();
+// cluster path (gi_cluster.cuh): S workspace of odd_ld(n)*n doubles per cluster, sized by the caller
+int gi_cluster_max_clusters(const GiPlan& plan);
+cudaError_t gi_cluster_launch(const GiBatch& B, const GiPlan& plan, double* Sws, int nclusters, cudaStream_t st);
 
 // K1 .. K7 of the batched LMPC engine.  Each returns the number of kernels it launched (>0) or a
 // negative cudaError_t.
