@@ -340,7 +340,7 @@ def main():
             p50_ms_per_batch=float(np.median(step_ms)), p50_us_per_solve_amortised=float(np.median(step_ms)) * 1e3 / batch,
             solved_ok=int(summary_all[:, 0].sum()), instances=world * batch,
             stage_ms=stage,
-            roofline=dict(kernel="gi_batch_kernel (K5+K6)", bound="hbm", achieved=achieved, peak=peak, unit="GB/s",
+            roofline=dict(kernel=("gi_small_kernel" if sz["nvar"] <= 64 else "gi_cluster_kernel / gi_batch_kernel") + " (K5+K6)", bound="hbm", achieved=achieved, peak=peak, unit="GB/s",
                           frac=achieved / peak, traffic=NCU_TRAFFIC.get((config, batch)), peak_source=peak_src,
                           fp64=dict(achieved_tflops=(k6_flops / solve_s / 1e12) if solve_s > 0 else 0.0, nominal_peak_tflops=FP64_PEAK_TFLOPS,
                                     frac=(k6_flops / solve_s / 1e12 / FP64_PEAK_TFLOPS) if solve_s > 0 else 0.0, mean_outer_iterations=mean_iters,

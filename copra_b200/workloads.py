@@ -1,8 +1,8 @@
 """Synthetic LMPC workloads C1..C5 (BASELINE.json `configs[0..4]`, definitions in SURVEY.md 8d).
 
 Deterministic: every random draw comes from SplitMix64 seeded with 0xC0B7A000 + 1000*config
-(+ `seed_offset`), stepped once per draw, instance-major.  The same generator is trivially
-restated in C++ (include/copra/workloads.hpp) so host-language callers see identical batches.
+(+ `seed_offset`), stepped once per draw, instance-major (SplitMix64 is a dozen lines in any host
+language, so C++ callers can regenerate identical batches).
 
 A *batch problem* is a dict:
     nx, nu, N, batch, initial_state,
