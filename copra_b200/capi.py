@@ -65,7 +65,7 @@ EXPORTS = ["copra_b200_abi_version", "copra_b200_device_count", "copra_b200_crea
            "copra_b200_last_error", "copra_b200_set_stream", "copra_b200_synchronize", "copra_b200_launch_count",
            "copra_b200_last_timing", "copra_b200_condense", "copra_b200_solve_qp_batch", "copra_b200_lmpc_sizes",
            "copra_b200_lmpc_run", "copra_b200_lmpc_build", "copra_b200_lmpc_solve", "copra_b200_lmpc_download",
-           "copra_b200_lmpc_results"]
+           "copra_b200_lmpc_results", "copra_b200_dgemm_batch"]
 
 _lib = None
 
@@ -104,6 +104,9 @@ def load():
         lib.copra_b200_lmpc_solve.argtypes = [C.c_void_p, C.POINTER(Results)]
         lib.copra_b200_lmpc_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         lib.copra_b200_lmpc_results.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        lib.copra_b200_dgemm_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int,
+                                               C.c_longlong, C.c_void_p, C.c_int, C.c_longlong, C.c_double, C.c_void_p, C.c_int,
+                                               C.c_longlong, C.c_int, C.c_int]
         _lib = lib
     return _lib
 
@@ -266,6 +269,21 @@ class Engine:
                                                  Phi.ctypes.data, Psi.ctypes.data if want_psi else None,
                                                  xi.ctypes.data, HOST))
         return np.swapaxes(Phi, 1, 2), (np.swapaxes(Psi, 1, 2) if want_psi else None), xi
+
+    # ---- dense assembly primitive (DMMA GEMM) ----
+    def dgemm(self, A, B, Cin=None, alpha=1.0, beta=0.0, trans_a=False):
+        """C = alpha * op(A) @ B + beta * Cin for arrays with a leading batch axis, logical (rows, cols) shapes."""
+        A, B = np.asarray(A, float), np.asarray(B, float)
+        batch = A.shape[0]
+        M = A.shape[2] if trans_a else A.shape[1]
+        K = A.shape[1] if trans_a else A.shape[2]
+        N = B.shape[2]
+        a, b = _colmajor(A, 2), _colmajor(B, 2)
+        c = _colmajor(np.zeros((batch, M, N)) if Cin is None else np.asarray(Cin, float), 2).copy()
+        self._check(self.lib.copra_b200_dgemm_batch(self.h, int(trans_a), M, N, K, float(alpha), a.ctypes.data, A.shape[1],
+                                                    A.shape[1] * A.shape[2], b.ctypes.data, K, K * N, float(beta), c.ctypes.data, M,
+                                                    M * N, batch, HOST))
+        return np.swapaxes(c, 1, 2)
 
     # ---- K5+K6 ----
     def solve_qp_batch(self, Q, c, Aeq, beq, Aineq, bineq, lb, ub):

@@ -699,6 +699,48 @@ int copra_b200_last_timing(const copra_b200_handle* hc, copra_b200_timing* t)
     return 0;
 }
 
+int copra_b200_dgemm_batch(copra_b200_handle* h, int transA, int M, int N, int K, double alpha, const double* A, int lda,
+    long long strideA, const double* B, int ldb, long long strideB, double beta, double* C, int ldc, long long strideC, int batch,
+    int memory)
+{
+    if (!h) return COPRA_B200_E_ARG;
+    if (M < 0 || N < 0 || K < 0 || batch <= 0 || !A || !B || !C) return fail(h, COPRA_B200_E_ARG, "bad GEMM arguments");
+    const int ar = transA ? K : M, ac = transA ? M : K;
+    if (lda < ar || ldb < K || ldc < M) return fail(h, COPRA_B200_E_ARG, "leading dimension too small");
+    CU(cudaSetDevice(h->device));
+    h->call_launches = 0;
+    const double *dA = A, *dB = B;
+    double* dC = C;
+    long long sA = strideA, sB = strideB, sC = strideC;
+    int rc;
+    if (memory == COPRA_B200_HOST) {
+        // pack each operand densely (ld == rows) and upload
+        const size_t nA = size_t(ar) * ac, nB = size_t(K) * N, nC = size_t(M) * N, Bz = batch;
+        std::vector<double> hA(nA * Bz), hB(nB * Bz), hC(nC * Bz);
+        for (size_t b = 0; b < Bz; ++b) {
+            for (int j = 0; j < ac; ++j) std::memcpy(&hA[b * nA + size_t(j) * ar], A + b * strideA + size_t(j) * lda, sizeof(double) * ar);
+            for (int j = 0; j < N; ++j) std::memcpy(&hB[b * nB + size_t(j) * K], B + b * strideB + size_t(j) * ldb, sizeof(double) * K);
+            for (int j = 0; j < N; ++j) std::memcpy(&hC[b * nC + size_t(j) * M], C + b * strideC + size_t(j) * ldc, sizeof(double) * M);
+        }
+        double *tA = nullptr, *tB = nullptr, *tC = nullptr;
+        if ((rc = ws(h, "gemm_A", nA * Bz, &tA))) return rc;
+        if ((rc = ws(h, "gemm_B", nB * Bz, &tB))) return rc;
+        if ((rc = ws(h, "gemm_C", nC * Bz, &tC))) return rc;
+        CU(cudaMemcpyAsync(tA, hA.data(), hA.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(tB, hB.data(), hB.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(tC, hC.data(), hC.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        LAUNCHED(dgemm_dmma_launch(transA, M, N, K, alpha, tA, ar, (long long)nA, tB, K, (long long)nB, beta, tC, M, (long long)nC, batch, h->stream));
+        CU(cudaMemcpyAsync(hC.data(), tC, hC.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (size_t b = 0; b < Bz; ++b)
+            for (int j = 0; j < N; ++j) std::memcpy(C + b * strideC + size_t(j) * ldc, &hC[b * nC + size_t(j) * M], sizeof(double) * M);
+        return 0;
+    }
+    LAUNCHED(dgemm_dmma_launch(transA, M, N, K, alpha, dA, lda, sA, dB, ldb, sB, beta, dC, ldc, sC, batch, h->stream));
+    return 0;
+}
+
 int copra_b200_lmpc_sizes(copra_b200_handle* h, const copra_b200_problem* p, copra_b200_sizes* s)
 {
     if (!h || !s) return COPRA_B200_E_ARG;

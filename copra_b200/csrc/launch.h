@@ -43,6 +43,9 @@ int k1_condense_launch(const BuildParams& P, cudaStream_t st);
 int k1_psi_fill_launch(const double* Gs, long long sGs, double* Psi, int nx, int nu, int N, int batch, cudaStream_t st);
 int k2k4_assemble_launch(const BuildParams& P, double* schur_ws, long long schur_stride, int sms, size_t smem_optin,
     cudaStream_t st);
+// batched FP64 tensor-core GEMM (dgemm_dmma.cu): C = alpha op(A) B + beta C, column-major; returns launches or -cudaError
+int dgemm_dmma_launch(int transA, int M, int N, int K, double alpha, const double* A, int lda, long long sA, const double* B, int ldb,
+    long long sB, double beta, double* C, int ldc, long long sC, int batch, cudaStream_t st);
 int k7_results_launch(const BuildParams& P, const double* x, double* control, double* trajectory, cudaStream_t st);
 
 } // namespace cb

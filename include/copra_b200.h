@@ -168,6 +168,14 @@ int copra_b200_solve_qp_batch(copra_b200_handle* h, int n, int meq, int m, int b
     copra_b200_array Aineq, copra_b200_array bineq, copra_b200_array lb, copra_b200_array ub,
     double* x, int* status, int* iters, int* nact, int* iact, int memory);
 
+/* Dense assembly primitive -- batched FP64 GEMM on the tensor cores (DMMA m8n8k4 fed through shared memory, TMA
+ * bulk loads for aligned operands): C[b] = alpha * op(A[b]) * B[b] + beta * C[b], column-major, strides in doubles.
+ * It is what full-size (autoSpan'd) entries use for M*Psi, T'WT, E*Psi (src/costFunctions.cpp:65-69,
+ * src/constraints.cpp:68-72); exported for callers that assemble their own dense terms. */
+int copra_b200_dgemm_batch(copra_b200_handle* h, int transA, int M, int N, int K, double alpha,
+    const double* A, int lda, long long strideA, const double* B, int ldb, long long strideB,
+    double beta, double* C, int ldc, long long strideC, int batch, int memory);
+
 /* Shape query / validation -- the dimension checks of initializeCost / initializeConstraint
  * (src/costFunctions.cpp:44-193, src/constraints.cpp:45-357); COPRA_B200_E_ARG == std::domain_error. */
 int copra_b200_lmpc_sizes(copra_b200_handle* h, const copra_b200_problem* p, copra_b200_sizes* s);

@@ -244,3 +244,19 @@ def test_cpp_facade_reference_scenarios():
     r = subprocess.run([exe, "gpu"], capture_output=True, text=True, timeout=600)
     print(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_dgemm_dmma_primitive(engine):
+    """the tensor-core FP64 GEMM behind full-size assembly: NN (TMA-fed when aligned) and TN, ragged and tiny shapes"""
+    rng = np.random.default_rng(11)
+    for (M, N, K, ta) in [(64, 64, 16, False), (128, 96, 64, False), (130, 70, 37, False), (5, 3, 2, False), (301, 300, 602, False),
+                          (64, 64, 16, True), (77, 33, 129, True), (300, 300, 602, True), (1, 50, 602, True)]:
+        A = rng.normal(size=(3, K, M) if ta else (3, M, K))
+        B = rng.normal(size=(3, K, N))
+        C0 = rng.normal(size=(3, M, N))
+        got = engine.dgemm(A, B, C0, alpha=0.7, beta=-1.3, trans_a=ta)
+        want = 0.7 * (np.swapaxes(A, 1, 2) if ta else A) @ B - 1.3 * C0
+        assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max()), (M, N, K, ta, np.abs(got - want).max())
+        got = engine.dgemm(A, B, trans_a=ta)
+        want = (np.swapaxes(A, 1, 2) if ta else A) @ B
+        assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max()), (M, N, K, ta)
