@@ -30,12 +30,12 @@ class Array(C.Structure):
 
 
 class Cost(C.Structure):
-    _fields_ = [("kind", C.c_int), ("rows", C.c_int), ("M", Array), ("N", Array), ("p", Array), ("w", Array)]
+    _fields_ = [("kind", C.c_int), ("rows", C.c_int), ("M", Array), ("N", Array), ("p", Array), ("w", Array), ("full_size", C.c_int)]
 
 
 class Constraint(C.Structure):
     _fields_ = [("kind", C.c_int), ("rows", C.c_int), ("is_ineq", C.c_int),
-                ("E", Array), ("G", Array), ("f", Array), ("lower", Array), ("upper", Array)]
+                ("E", Array), ("G", Array), ("f", Array), ("lower", Array), ("upper", Array), ("full_size", C.c_int)]
 
 
 class Problem(C.Structure):
@@ -145,10 +145,13 @@ class HostBatch:
             costs[i].kind = COST_KINDS[c["kind"]]
             pv = np.asarray(c["p"])
             costs[i].rows = int(pv.shape[-1])
+            nx_, nu_ = int(bp["nx"]), int(bp["nu"])
             if c.get("M") is not None:
                 costs[i].M = self._arr("M", c["M"])
+                costs[i].full_size = int(np.asarray(c["M"]).shape[-1] != nx_)
             if c.get("N") is not None:
                 costs[i].N = self._arr("N", c["N"])
+                costs[i].full_size = int(np.asarray(c["N"]).shape[-1] != nu_) if c.get("M") is None else costs[i].full_size
             costs[i].p = self._arr("p", c["p"])
             w = c.get("w")
             w = np.ones(costs[i].rows) if w is None else np.asarray(w, dtype=np.float64)
@@ -165,14 +168,18 @@ class HostBatch:
             cstrs[i].is_ineq = int(bool(c.get("is_ineq", True)))
             if c["kind"] in ("trajectory_bound", "control_bound"):
                 cstrs[i].rows = int(np.asarray(c["lower"]).shape[-1])
+                cstrs[i].full_size = int(cstrs[i].rows != (int(bp["nx"]) if c["kind"] == "trajectory_bound" else int(bp["nu"])))
                 cstrs[i].lower = self._arr("lower", c["lower"])
                 cstrs[i].upper = self._arr("upper", c["upper"])
             else:
                 cstrs[i].rows = int(np.asarray(c["f"]).shape[-1])
                 if c.get("E") is not None:
                     cstrs[i].E = self._arr("E", c["E"])
+                    cstrs[i].full_size = int(np.asarray(c["E"]).shape[-1] != int(bp["nx"]))
                 if c.get("G") is not None:
                     cstrs[i].G = self._arr("G", c["G"])
+                    if c.get("E") is None:
+                        cstrs[i].full_size = int(np.asarray(c["G"]).shape[-1] != int(bp["nu"]))
                 cstrs[i].f = self._arr("f", c["f"])
         self.keep.append(cstrs)
         p.ncstr, p.cstrs = len(bp["constraints"]), cstrs

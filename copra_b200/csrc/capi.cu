@@ -217,8 +217,9 @@ int run_download(copra_b200_handle* h, Download& D, int memory)
 // ---- problem description -> families ----------------------------------------------------------
 struct Plan {
     Sizes sz;
-    struct CostMeta { int kind, rows, i0, i1, hasM, hasN; };
-    struct FamMeta { int cstr, rows, i0, i1, hasE, hasG, is_eq, row_off, which; std::vector<int> lines; };
+    struct CostMeta { int kind, rows, i0, i1, hasM, hasN, dense; };
+    struct FamMeta { int cstr, rows, i0, i1, hasE, hasG, is_eq, row_off, which, dense, gather; std::vector<int> lines; };
+    int cb_full = 0;
     std::vector<CostMeta> costs;
     std::vector<FamMeta> fams;
     int bound_cstr = -1;
@@ -250,7 +251,7 @@ int make_plan(copra_b200_handle* h, const copra_b200_problem* p, Plan& pl)
     for (int i = 0; i < p->ncost; ++i) {
         const copra_b200_cost& c = p->costs[i];
         if (c.rows <= 0 || !c.p.ptr) return fail(h, COPRA_B200_E_ARG, "cost %d: rows must be positive and p given", i);
-        Plan::CostMeta m{ c.kind, c.rows, 0, 0, 0, 0 };
+        Plan::CostMeta m{ c.kind, c.rows, 0, 0, 0, 0, c.full_size ? 1 : 0 };
         switch (c.kind) {
         case COPRA_B200_COST_TRAJECTORY: m.i0 = 0; m.i1 = N + 1; m.hasM = 1; break;
         case COPRA_B200_COST_TARGET: m.i0 = N; m.i1 = N + 1; m.hasM = 1; break;
@@ -261,15 +262,23 @@ int make_plan(copra_b200_handle* h, const copra_b200_problem* p, Plan& pl)
         if (m.hasM && !c.M.ptr) return fail(h, COPRA_B200_E_ARG, "cost %d: M is required", i);
         if (m.hasN && !c.N.ptr) return fail(h, COPRA_B200_E_ARG, "cost %d: N is required", i);
         if (!c.w.ptr) return fail(h, COPRA_B200_E_ARG, "cost %d: weights are required (copra default: ones)", i);
+        if (m.dense) {
+            if (c.kind == COPRA_B200_COST_TARGET) return fail(h, COPRA_B200_E_ARG, "cost %d: TargetCost takes a step-size M (xDim columns) only", i);
+            m.i0 = 0; m.i1 = 1; // one stacked block
+        }
         pl.costs.push_back(m);
     }
     int eq_off = 0, in_off = 0;
     for (int i = 0; i < p->ncstr; ++i) {
         const copra_b200_constraint& c = p->cstrs[i];
         if (c.rows <= 0) return fail(h, COPRA_B200_E_ARG, "constraint %d: rows must be positive", i);
+        const bool full = c.full_size != 0;
         auto push = [&](int i0, int i1, int hasE, int hasG, bool iseq, int which, std::vector<int> lines) {
             Plan::FamMeta f;
             f.cstr = i; f.rows = lines.empty() ? c.rows : int(lines.size());
+            f.dense = (full && which == 0) ? 1 : 0;
+            f.gather = (full && which != 0) ? 1 : 0;
+            if (full) { i0 = 0; i1 = 1; }
             f.i0 = i0; f.i1 = i1; f.hasE = hasE; f.hasG = hasG; f.is_eq = iseq ? 1 : 0; f.which = which;
             f.lines = std::move(lines);
             int& off = iseq ? eq_off : in_off;
@@ -292,26 +301,27 @@ int make_plan(copra_b200_handle* h, const copra_b200_problem* p, Plan& pl)
             break;
         case COPRA_B200_CSTR_TRAJECTORY_BOUND: {
             if (!c.lower.ptr || !c.upper.ptr) return fail(h, COPRA_B200_E_ARG, "constraint %d: lower and upper are required", i);
-            if (c.rows != nx) return fail(h, COPRA_B200_E_ARG, "constraint %d: trajectory bounds must have nx rows (step-size entry)", i);
+            const int brows = full ? pl.sz.X : nx;
+            if (c.rows != brows) return fail(h, COPRA_B200_E_ARG, "constraint %d: trajectory bounds must have xDim (or fullXDim) rows", i);
             // line selection (include/constraints.h:247-254) is part of the problem SHAPE: it is taken
             // from instance 0 and, for host inputs, verified to be the same for every instance.
             std::vector<int> ll, ul;
-            copra_b200_handle::TbKey key{ c.lower.ptr, c.upper.ptr, nx };
+            copra_b200_handle::TbKey key{ c.lower.ptr, c.upper.ptr, brows };
             auto hit = h->tb_cache.find(key);
             if (p->memory == COPRA_B200_DEVICE && hit != h->tb_cache.end()) {
                 ll = hit->second.first;
                 ul = hit->second.second;
             } else {
                 std::vector<double> lo, up;
-                int rc = fetch_host(h, c.lower, nx, p->memory, lo);
+                int rc = fetch_host(h, c.lower, brows, p->memory, lo);
                 if (rc) return rc;
-                rc = fetch_host(h, c.upper, nx, p->memory, up);
+                rc = fetch_host(h, c.upper, brows, p->memory, up);
                 if (rc) return rc;
-                for (int l = 0; l < nx; ++l) if (lo[l] != -INFINITY) ll.push_back(l);
-                for (int l = 0; l < nx; ++l) if (up[l] != INFINITY) ul.push_back(l);
+                for (int l = 0; l < brows; ++l) if (lo[l] != -INFINITY) ll.push_back(l);
+                for (int l = 0; l < brows; ++l) if (up[l] != INFINITY) ul.push_back(l);
                 if (p->memory == COPRA_B200_HOST) {
                     for (int b = 1; b < p->batch; ++b)
-                        for (int l = 0; l < nx; ++l) {
+                        for (int l = 0; l < brows; ++l) {
                             const double a = c.lower.ptr[(long long)b * c.lower.stride + l], u = c.upper.ptr[(long long)b * c.upper.stride + l];
                             if ((a != -INFINITY) != (lo[l] != -INFINITY) || (u != INFINITY) != (up[l] != INFINITY))
                                 return fail(h, COPRA_B200_E_ARG, "constraint %d: the set of infinite trajectory bounds must be the same for every instance", i);
@@ -323,7 +333,8 @@ int make_plan(copra_b200_handle* h, const copra_b200_problem* p, Plan& pl)
         } break;
         case COPRA_B200_CSTR_CONTROL_BOUND:
             if (!c.lower.ptr || !c.upper.ptr) return fail(h, COPRA_B200_E_ARG, "constraint %d: lower and upper are required", i);
-            if (c.rows != nu) return fail(h, COPRA_B200_E_ARG, "constraint %d: control bounds must have nu rows (step-size entry)", i);
+            if (c.rows != (full ? pl.sz.nU : nu)) return fail(h, COPRA_B200_E_ARG, "constraint %d: control bounds must have uDim (or fullUDim) rows", i);
+            pl.cb_full = full ? 1 : 0;
             if (pl.bound_cstr >= 0) return fail(h, COPRA_B200_E_UNSUPPORTED, "only one ControlBoundConstraint per controller (reference quirk Q8)");
             pl.bound_cstr = i;
             break;
@@ -419,15 +430,15 @@ int do_build(copra_b200_handle* h, const copra_b200_problem* p)
         if (f.which == 0) continue;
         sel_off[k] = sel.size();
         line_off[k] = lines.size();
-        sel.resize(sel.size() + size_t(f.rows) * nx, 0.0);
+        if (!f.gather) sel.resize(sel.size() + size_t(f.rows) * nx, 0.0);
         for (int l = 0; l < f.rows; ++l) {
-            sel[sel_off[k] + l + size_t(f.lines[l]) * f.rows] = 1.0;
+            if (!f.gather) sel[sel_off[k] + l + size_t(f.lines[l]) * f.rows] = 1.0;
             lines.push_back(f.lines[l]);
         }
     }
     double* d_sel = nullptr;
     int* d_lines = nullptr;
-    if (!sel.empty()) {
+    if (!lines.empty()) {
         rc = ws(h, "sel", sel.size(), &d_sel); if (rc) return rc;
         rc = ws(h, "lines", lines.size(), &d_lines); if (rc) return rc;
         if (sel != h->sel_host || lines != h->lines_host) {
@@ -456,8 +467,9 @@ int do_build(copra_b200_handle* h, const copra_b200_problem* p)
         const copra_b200_cost& c = p->costs[i];
         CostFam& F = P.cost[i];
         F.rows = c.rows; F.i0 = pl.costs[i].i0; F.i1 = pl.costs[i].i1; F.hasM = pl.costs[i].hasM; F.hasN = pl.costs[i].hasN;
-        if (F.hasM) U.add(c.M, size_t(c.rows) * nx, &F.M);
-        if (F.hasN) U.add(c.N, size_t(c.rows) * nu, &F.N);
+        F.dense = pl.costs[i].dense;
+        if (F.hasM) U.add(c.M, size_t(c.rows) * (F.dense ? pl.sz.X : nx), &F.M);
+        if (F.hasN) U.add(c.N, size_t(c.rows) * (F.dense ? pl.sz.nU : nu), &F.N);
         U.add(c.p, c.rows, &F.p);
         U.add(c.w, c.rows, &F.w);
     }
@@ -475,10 +487,11 @@ int do_build(copra_b200_handle* h, const copra_b200_problem* p)
         const copra_b200_constraint& c = p->cstrs[f.cstr];
         CstrFam& F = P.fam[k];
         F.rows = f.rows; F.i0 = f.i0; F.i1 = f.i1; F.hasE = f.hasE; F.hasG = f.hasG; F.is_eq = f.is_eq; F.row_off = f.row_off;
+        F.dense = f.dense; F.gather = f.gather;
         F.fidx = nullptr;
         if (f.which == 0) {
-            if (f.hasE) U.add(c.E, size_t(c.rows) * nx, &F.E);
-            if (f.hasG) U.add(c.G, size_t(c.rows) * nu, &F.G);
+            if (f.hasE) U.add(c.E, size_t(c.rows) * (f.dense ? pl.sz.X : nx), &F.E);
+            if (f.hasG) U.add(c.G, size_t(c.rows) * (f.dense ? pl.sz.nU : nu), &F.G);
             U.add(c.f, c.rows, &F.f);
         }
     }
@@ -488,7 +501,7 @@ int do_build(copra_b200_handle* h, const copra_b200_problem* p)
         const auto& f = pl.fams[k];
         if (f.which == 0) continue;
         CstrFam& F = P.fam[k];
-        F.E.p = d_sel + sel_off[k];
+        F.E.p = f.gather ? nullptr : d_sel + sel_off[k];
         F.E.s = 0;
         F.f = f.which == 1 ? lowerArr[f.cstr] : upperArr[f.cstr];
         F.fidx = d_lines + line_off[k];
@@ -496,6 +509,7 @@ int do_build(copra_b200_handle* h, const copra_b200_problem* p)
     if (pl.bound_cstr >= 0) {
         P.cb_lower = lowerArr[pl.bound_cstr];
         P.cb_upper = upperArr[pl.bound_cstr];
+        P.cb_full = pl.cb_full;
     }
     rc = record(h, 1);
     if (rc) return rc;
@@ -527,6 +541,19 @@ int do_build(copra_b200_handle* h, const copra_b200_problem* p)
         snprintf(nm, sizeof nm, "res%d", i); if ((rc = ws(h, nm, Bz * F.sres, &F.res))) return rc;
         snprintf(nm, sizeof nm, "Ec%d", i); if ((rc = ws(h, nm, Bz * F.sE, &F.E))) return rc;
         snprintf(nm, sizeof nm, "fc%d", i); if ((rc = ws(h, nm, Bz * F.sf, &F.f))) return rc;
+        F.T = F.WT = nullptr; F.sT = 0;
+        if (F.dense) {
+            F.sT = (long long)(r * nU);
+            snprintf(nm, sizeof nm, "Tc%d", i); if ((rc = ws(h, nm, Bz * F.sT, &F.T))) return rc;
+            snprintf(nm, sizeof nm, "WTc%d", i); if ((rc = ws(h, nm, Bz * F.sT, &F.WT))) return rc;
+        }
+    }
+    {
+        bool need_psi = false;
+        for (int i = 0; i < P.ncost; ++i) need_psi |= P.cost[i].dense && P.cost[i].hasM;
+        for (int k = 0; k < P.nfam; ++k) need_psi |= P.fam[k].dense && P.fam[k].hasE;
+        P.PsiFull = nullptr;
+        if (need_psi && (rc = ws(h, "Psi", Bz * X * nU, &P.PsiFull))) return rc;
     }
     for (int k = 0; k < P.nfam; ++k) {
         CstrFam& F = P.fam[k];

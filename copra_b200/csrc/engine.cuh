@@ -27,6 +27,10 @@ struct DArr { // (pointer, batch stride) on the device
 };
 
 struct CostFam {
+    int dense;      // 1: full-size entry: M is rows x X, N rows x nU; evaluated by the DMMA GEMM path
+    double* T;      // dense: rows x nU   T = M Psi (+ N)
+    double* WT;     // dense: rows x nU   diag(w) T
+    long long sT;
     int rows;       // r
     int i0, i1;     // step range
     int hasM, hasN;
@@ -41,6 +45,8 @@ struct CostFam {
 };
 
 struct CstrFam {
+    int dense;      // 1: full-size entry (E rows x X, G rows x nU): rows = E Psi + G by the DMMA GEMM path
+    int gather;     // 1: rows are copies of Psi/Phi/xi rows fidx[] (full-size TrajectoryBoundConstraint)
     int rows;       // r
     int i0, i1;
     int hasE, hasG;
@@ -61,6 +67,8 @@ struct BuildParams {
     DArr A, B, d, x0;
     DArr R, r, x0lb, x0ub;        // initial-state mode (p may be null)
     DArr cb_lower, cb_upper;      // ControlBoundConstraint (p null = none)
+    int cb_full;                  // 1: lower/upper hold nU entries (full-size entry)
+    double* PsiFull;              // X x nU per instance, only materialised when a full-size entry needs it
     // K1 outputs (workspace, per instance)
     double* Phi;   // X x nx
     double* Gs;    // (N*nx) x nu  == Psi[nx:, 0:nu]

@@ -146,6 +146,7 @@ __global__ void k2_precompute_kernel(const __grid_constant__ BuildParams P)
         const double* xi = P.xi + (long long)b * X;
         for (int ci = 0; ci < P.ncost; ++ci) {
             const CostFam& F = P.cost[ci];
+            if (F.dense) continue; // full-size entry: DMMA GEMM path
             const int r = F.rows, ns = F.i1 - F.i0;
             const double* M = F.hasM ? F.M.at(b) : nullptr;
             const double* Nn = F.hasN ? F.N.at(b) : nullptr;
@@ -185,6 +186,7 @@ __global__ void k2_precompute_kernel(const __grid_constant__ BuildParams P)
         }
         for (int fi = 0; fi < P.nfam; ++fi) {
             const CstrFam& F = P.fam[fi];
+            if (F.dense || F.gather) continue;
             const int r = F.rows, ns = F.i1 - F.i0;
             const double* E = F.hasE ? F.E.at(b) : nullptr;
             const double* G = F.hasG ? F.G.at(b) : nullptr;
@@ -259,6 +261,7 @@ __global__ void k2_assemble_q_kernel(const __grid_constant__ BuildParams P)
         double val = (dd == 0 && a == bb) ? P.qdiag : 0.0;
         for (int ci = 0; ci < P.ncost; ++ci) {
             const CostFam& F = P.cost[ci];
+            if (F.dense) continue; // added afterwards by the GEMM path (Q += T'WT)
             const int r = F.rows;
             // steps i in [max(i0,jmax), i1-1]  <->  kk = i - jmax
             const int kk_hi = F.i1 - 1 - jmax;
@@ -309,6 +312,7 @@ __global__ void k2_assemble_ef_kernel(const __grid_constant__ BuildParams P)
     const int s = rem % (nx + 1), col = rem / (nx + 1);
     const int j = col / nu, bb = col % nu;
     const CostFam& F = P.cost[ci];
+    if (F.dense) return;
     const int r = F.rows;
     const double* MG = F.MGx + (long long)b * F.sMGx;
     const double* MPhi = F.MPhi + (long long)b * F.sMPhi;
@@ -351,20 +355,98 @@ __global__ void k3_fill_rows_kernel(const __grid_constant__ BuildParams P)
     }
     if (fi < 0) return;
     const CstrFam& F = P.fam[fi];
-    const int r = F.rows;
-    const int i = F.i0 + (lrow - F.row_off) / r, l = (lrow - F.row_off) % r;
-    const double* EGx = F.EGx + (long long)b * F.sEGx;
     double* Aout = (iseq ? P.Aeq : P.Aineq) + (long long)b * mtot * nvar;
     if (off) {
         const double* Y = (iseq ? P.Yeq : P.Yin) + (long long)b * mtot * nx;
         for (int s = 0; s < nx; ++s) Aout[lrow + (long long)s * mtot] = Y[lrow + (long long)s * mtot];
     }
+    if (F.dense || F.gather) return; // rows written by the GEMM / gather path
+    const int r = F.rows;
+    const int i = F.i0 + (lrow - F.row_off) / r, l = (lrow - F.row_off) % r;
+    const double* EGx = F.EGx + (long long)b * F.sEGx;
     for (int j = 0; j < N; ++j) {
         const int kk = i - j;
         for (int bb = 0; bb < nu; ++bb) {
             const double v = (kk >= 0) ? EGx[l + r * (bb + nu * kk)] : 0.0;
             Aout[lrow + (long long)(off + j * nu + bb) * mtot] = v;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Full-size (autoSpan'd) entries: epilogues around the DMMA GEMMs (dgemm_dmma.cu).
+//   cost : T (rows x nU) holds M Psi; T += N (or T = N); WT = diag(w) T; res = M xi - p (or -p); MPhi = 0 without M
+//          (src/costFunctions.cpp:65-71,141-146,197-203)
+//   cstr : A rows hold E Psi; A += G (or A = G); z = f - E xi (or f); Y = 0 without E   (src/constraints.cpp:68-73,199-204)
+// grid = (element tiles, batch)
+// ------------------------------------------------------------------------------------------------
+__global__ void k2_dense_cost_epilogue_kernel(const __grid_constant__ BuildParams P, int ci)
+{
+    const CostFam& F = P.cost[ci];
+    const int b = blockIdx.y, R = F.rows, nU = P.nU, nx = P.nx;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)R * nU) return;
+    const int r = int(t % R), c = int(t / R);
+    double* T = F.T + (long long)b * F.sT;
+    double* WT = F.WT + (long long)b * F.sT;
+    double v = F.hasM ? T[t] : 0.0;
+    if (F.hasN) v = F.hasM ? add_(v, F.N.at(b)[t]) : F.N.at(b)[t];
+    T[t] = v;
+    WT[t] = mul_(F.w.at(b)[r], v);
+    if (c == 0) {
+        double* res = F.res + (long long)b * F.sres;
+        res[r] = F.hasM ? add_(res[r], -F.p.at(b)[r]) : -F.p.at(b)[r];
+        if (!F.hasM) {
+            double* MPhi = F.MPhi + (long long)b * F.sMPhi;
+            for (int s = 0; s < nx; ++s) MPhi[r + (long long)s * R] = 0.0;
+        }
+    }
+}
+
+__global__ void k3_dense_cstr_epilogue_kernel(const __grid_constant__ BuildParams P, int fi)
+{
+    const CstrFam& F = P.fam[fi];
+    const int b = blockIdx.y, R = F.rows, nU = P.nU, nx = P.nx, nvar = P.nvar;
+    const int off = P.initial_state ? nx : 0;
+    const int mtot = F.is_eq ? P.meq : P.mineq;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)R * nU) return;
+    const int r = int(t % R), c = int(t / R);
+    double* Aout = (F.is_eq ? P.Aeq : P.Aineq) + (long long)b * mtot * nvar + F.row_off + (long long)off * mtot;
+    double v = F.hasE ? Aout[r + (long long)c * mtot] : 0.0;
+    if (F.hasG) v = F.hasE ? add_(v, F.G.at(b)[t]) : F.G.at(b)[t];
+    Aout[r + (long long)c * mtot] = v;
+    if (c == 0) {
+        double* z = (F.is_eq ? P.zeq : P.zin) + (long long)b * mtot + F.row_off;
+        z[r] = F.hasE ? add_(F.f.at(b)[r], -z[r]) : F.f.at(b)[r];
+        if (!F.hasE) {
+            double* Y = (F.is_eq ? P.Yeq : P.Yin) + (long long)b * mtot * nx + F.row_off;
+            for (int s = 0; s < nx; ++s) Y[r + (long long)s * mtot] = 0.0;
+        }
+    }
+}
+
+// full-size TrajectoryBoundConstraint: rows are copies of rows fidx[] of Psi / Phi / xi (src/constraints.cpp:288-314)
+__global__ void k3_gather_rows_kernel(const __grid_constant__ BuildParams P, int fi)
+{
+    const CstrFam& F = P.fam[fi];
+    const int b = blockIdx.y, R = F.rows, nU = P.nU, nx = P.nx, nu = P.nu, N = P.N, X = P.X, nvar = P.nvar;
+    const int off = P.initial_state ? nx : 0;
+    const int mtot = F.is_eq ? P.meq : P.mineq;
+    const long long NX = (long long)N * nx;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)R * nU) return;
+    const int r = int(t % R), col = int(t / R);
+    const int idx = F.fidx[r], i = idx / nx, l = idx % nx, j = col / nu, c = col % nu;
+    const double* Gs = P.Gs + (long long)b * NX * nu;
+    double* Aout = (F.is_eq ? P.Aeq : P.Aineq) + (long long)b * mtot * nvar + F.row_off + (long long)off * mtot;
+    Aout[r + (long long)col * mtot] = (i > j) ? Gs[(long long)(i - 1 - j) * nx + l + (long long)c * NX] : 0.0;
+    if (col == 0) {
+        const double* Phi = P.Phi + (long long)b * X * nx;
+        double* Y = (F.is_eq ? P.Yeq : P.Yin) + (long long)b * mtot * nx + F.row_off;
+        double* z = (F.is_eq ? P.zeq : P.zin) + (long long)b * mtot + F.row_off;
+        for (int s = 0; s < nx; ++s) Y[r + (long long)s * mtot] = Phi[idx + (long long)s * X];
+        z[r] = add_(F.f.at(b)[idx], -P.xi[(long long)b * X + idx]);
     }
 }
 
@@ -422,8 +504,8 @@ __global__ void k4_finalize_kernel(const __grid_constant__ BuildParams P)
         double* lb = P.lb + (long long)b * nvar;
         double* ub = P.ub + (long long)b * nvar;
         for (int k = tid; k < nU; k += T) {
-            lb[off + k] = P.cb_lower.p ? P.cb_lower.at(b)[k % nu] : -DBL_MAX;
-            ub[off + k] = P.cb_upper.p ? P.cb_upper.at(b)[k % nu] : DBL_MAX;
+            lb[off + k] = P.cb_lower.p ? P.cb_lower.at(b)[P.cb_full ? k : k % nu] : -DBL_MAX;
+            ub[off + k] = P.cb_upper.p ? P.cb_upper.at(b)[P.cb_full ? k : k % nu] : DBL_MAX;
         }
         if (P.initial_state) {
             for (int k = tid; k < nx; k += T) {
@@ -521,27 +603,79 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
         ++launches;                               \
     } while (0)
 
+#define CB_GEMM(...)                                   \
+    do {                                               \
+        int n_ = dgemm_dmma_launch(__VA_ARGS__);       \
+        if (n_ < 0) return n_;                         \
+        launches += n_;                                \
+    } while (0)
+
 int k2k4_assemble_launch(const BuildParams& P, double* schur_ws, long long schur_stride, int sms, size_t smem_optin, cudaStream_t st)
 {
     int launches = 0;
+    if (P.batch > 65535) return -int(cudaErrorInvalidValue); // gridDim.y limit: the C API chunks larger batches
     const int pgrid = std::min(P.batch, sms * 8);
+    const int nb = P.batch, nx = P.nx, nU = P.nU, X = P.X, nvar = P.nvar;
+    const int off = P.initial_state ? nx : 0;
+    bool any_dense = false;
+    for (int i = 0; i < P.ncost; ++i) any_dense |= P.cost[i].dense && P.cost[i].hasM;
+    for (int k = 0; k < P.nfam; ++k) any_dense |= P.fam[k].dense && P.fam[k].hasE;
     k2_precompute_kernel<<<pgrid, 128, 0, st>>>(P);
     CB_CHECK_LAUNCH();
-    if (P.batch > 65535) return -int(cudaErrorInvalidValue); // gridDim.y limit: the C API chunks larger batches
+    if (any_dense) { // dense M / E blocks multiply the materialised Psi
+        int n_ = k1_psi_fill_launch(P.Gs, (long long)P.N * nx * P.nu, P.PsiFull, nx, P.nu, P.N, nb, st);
+        if (n_ < 0) return n_;
+        launches += n_;
+    }
     {
-        const int nb = P.batch;
         const int nchain = (2 * P.N - 1) * P.nu * P.nu;
         k2_assemble_q_kernel<<<dim3(ceil_div(nchain, 128), nb), 128, 0, st>>>(P);
         CB_CHECK_LAUNCH();
-        if (P.ncost > 0) {
-            const int nef = (P.nx + 1) * P.nU * P.ncost;
-            k2_assemble_ef_kernel<<<dim3(ceil_div(nef, 128), nb), 128, 0, st>>>(P);
-            CB_CHECK_LAUNCH();
+    }
+    const long long sPsi = (long long)X * nU, sPhi = (long long)X * nx;
+    for (int ci = 0; ci < P.ncost; ++ci) { // full-size costs: T = M Psi (+N), Q += T'WT, E = (M Phi)'WT, f = res'WT
+        const CostFam& F = P.cost[ci];
+        if (!F.dense) continue;
+        const int R = F.rows;
+        if (F.hasM) {
+            CB_GEMM(0, R, nU, X, 1.0, F.M.p, R, F.M.s, P.PsiFull, X, sPsi, 0.0, F.T, R, F.sT, nb, st);
+            CB_GEMM(0, R, nx, X, 1.0, F.M.p, R, F.M.s, P.Phi, X, sPhi, 0.0, F.MPhi, R, F.sMPhi, nb, st);
+            CB_GEMM(0, R, 1, X, 1.0, F.M.p, R, F.M.s, P.xi, X, (long long)X, 0.0, F.res, R, F.sres, nb, st);
         }
-        if (P.meq + P.mineq > 0) {
-            k3_fill_rows_kernel<<<dim3(ceil_div(P.meq + P.mineq, 128), nb), 128, 0, st>>>(P);
+        k2_dense_cost_epilogue_kernel<<<dim3(ceil_div(R * nU, 256), nb), 256, 0, st>>>(P, ci);
+        CB_CHECK_LAUNCH();
+        CB_GEMM(1, nU, nU, R, 1.0, F.T, R, F.sT, F.WT, R, F.sT, 1.0, P.Q + off + (long long)off * nvar, nvar, (long long)nvar * nvar, nb, st);
+        CB_GEMM(1, nx, nU, R, 1.0, F.MPhi, R, F.sMPhi, F.WT, R, F.sT, 0.0, F.E, nx, F.sE, nb, st);
+        CB_GEMM(1, 1, nU, R, 1.0, F.res, R, F.sres, F.WT, R, F.sT, 0.0, F.f, 1, F.sf, nb, st);
+    }
+    if (P.ncost > 0) {
+        const int nef = (nx + 1) * nU * P.ncost;
+        k2_assemble_ef_kernel<<<dim3(ceil_div(nef, 128), nb), 128, 0, st>>>(P);
+        CB_CHECK_LAUNCH();
+    }
+    for (int fi = 0; fi < P.nfam; ++fi) { // full-size constraints: rows = E Psi (+G), Y = E Phi, z = f - E xi
+        const CstrFam& F = P.fam[fi];
+        if (!F.dense && !F.gather) continue;
+        const int R = F.rows, mtot = F.is_eq ? P.meq : P.mineq;
+        double* Aout = (F.is_eq ? P.Aeq : P.Aineq) + F.row_off + (long long)off * mtot;
+        double* Y = (F.is_eq ? P.Yeq : P.Yin) + F.row_off;
+        double* z = (F.is_eq ? P.zeq : P.zin) + F.row_off;
+        if (F.gather) {
+            k3_gather_rows_kernel<<<dim3(ceil_div(R * nU, 256), nb), 256, 0, st>>>(P, fi);
             CB_CHECK_LAUNCH();
+            continue;
         }
+        if (F.hasE) {
+            CB_GEMM(0, R, nU, X, 1.0, F.E.p, R, F.E.s, P.PsiFull, X, sPsi, 0.0, Aout, mtot, (long long)mtot * nvar, nb, st);
+            CB_GEMM(0, R, nx, X, 1.0, F.E.p, R, F.E.s, P.Phi, X, sPhi, 0.0, Y, mtot, (long long)mtot * nx, nb, st);
+            CB_GEMM(0, R, 1, X, 1.0, F.E.p, R, F.E.s, P.xi, X, (long long)X, 0.0, z, mtot, (long long)mtot, nb, st);
+        }
+        k3_dense_cstr_epilogue_kernel<<<dim3(ceil_div(R * nU, 256), nb), 256, 0, st>>>(P, fi);
+        CB_CHECK_LAUNCH();
+    }
+    if (P.meq + P.mineq > 0) {
+        k3_fill_rows_kernel<<<dim3(ceil_div(P.meq + P.mineq, 128), nb), 128, 0, st>>>(P);
+        CB_CHECK_LAUNCH();
     }
     k4_finalize_kernel<<<pgrid, 128, 0, st>>>(P);
     CB_CHECK_LAUNCH();

@@ -13,9 +13,8 @@
 // batched entry point).  All numerics run in the sm_100a kernels behind include/copra_b200.h; this
 // header only validates shapes, packs pointers and copies results -- there is no CPU compute path.
 //
-// Scope: step-size entries are evaluated on the GPU; full-size (autoSpan'd) entries are
-// accepted by the shape logic (addCost / addConstraint never throw for them, like the reference) but
-// solve()/update() reports std::runtime_error until the dense DMMA assembly path lands (row N2).
+// Step-size entries use the structured (block-Toeplitz) assembly kernels; full-size (autoSpan'd) entries are
+// dense R x X blocks and go through the FP64 tensor-core GEMM (dgemm_dmma.cu).
 #pragma once
 
 #if defined(__has_include)
@@ -237,7 +236,6 @@ public:
     // Evaluate this cost alone on the GPU (K1 + K2 with one cost family): Q(), c(), E(), f().
     virtual void update(const PreviewSystem& ps)
     {
-        if (fullSizeEntry_) COPRA_RUNTIME_ERROR("full-size (autoSpan'd) cost entries are not evaluated on the B200 path yet");
         b200::Description D;
         D.system(ps);
         D.p.flags = COPRA_B200_FLAG_NO_REG;
@@ -301,7 +299,7 @@ public:
     copra_b200_cost describe() const override
     {
         copra_b200_cost c{};
-        c.kind = COPRA_B200_COST_TRAJECTORY; c.rows = int(M_.rows());
+        c.kind = COPRA_B200_COST_TRAJECTORY; c.rows = int(M_.rows()); c.full_size = fullSizeEntry_;
         c.M = b200::arr(M_.data()); c.p = b200::arr(p_.data()); c.w = b200::arr(weights_.data());
         return c;
     }
@@ -360,7 +358,7 @@ public:
     copra_b200_cost describe() const override
     {
         copra_b200_cost c{};
-        c.kind = COPRA_B200_COST_CONTROL; c.rows = int(N_.rows());
+        c.kind = COPRA_B200_COST_CONTROL; c.rows = int(N_.rows()); c.full_size = fullSizeEntry_;
         c.N = b200::arr(N_.data()); c.p = b200::arr(p_.data()); c.w = b200::arr(weights_.data());
         return c;
     }
@@ -397,7 +395,7 @@ public:
     copra_b200_cost describe() const override
     {
         copra_b200_cost c{};
-        c.kind = COPRA_B200_COST_MIXED; c.rows = int(M_.rows());
+        c.kind = COPRA_B200_COST_MIXED; c.rows = int(M_.rows()); c.full_size = fullSizeEntry_;
         c.M = b200::arr(M_.data()); c.N = b200::arr(N_.data()); c.p = b200::arr(p_.data()); c.w = b200::arr(weights_.data());
         return c;
     }
@@ -445,7 +443,6 @@ public:
     // Evaluate this constraint alone on the GPU (K1 + K3 + K4 with one family): A(), b(), Y(), z().
     void update(const PreviewSystem& ps) override
     {
-        if (fullSizeEntry_) COPRA_RUNTIME_ERROR("full-size (autoSpan'd) constraint entries are not evaluated on the B200 path yet");
         b200::Description D;
         D.system(ps);
         D.cstrs.push_back(describe());
@@ -498,7 +495,7 @@ public:
     copra_b200_constraint describe() const override
     {
         copra_b200_constraint c{};
-        c.kind = COPRA_B200_CSTR_TRAJECTORY; c.rows = int(E_.rows()); c.is_ineq = isIneq_;
+        c.kind = COPRA_B200_CSTR_TRAJECTORY; c.rows = int(E_.rows()); c.is_ineq = isIneq_; c.full_size = fullSizeEntry_;
         c.E = b200::arr(E_.data()); c.f = b200::arr(f_.data());
         return c;
     }
@@ -537,7 +534,7 @@ public:
     copra_b200_constraint describe() const override
     {
         copra_b200_constraint c{};
-        c.kind = COPRA_B200_CSTR_CONTROL; c.rows = int(G_.rows()); c.is_ineq = isIneq_;
+        c.kind = COPRA_B200_CSTR_CONTROL; c.rows = int(G_.rows()); c.is_ineq = isIneq_; c.full_size = fullSizeEntry_;
         c.G = b200::arr(G_.data()); c.f = b200::arr(f_.data());
         return c;
     }
@@ -577,7 +574,7 @@ public:
     copra_b200_constraint describe() const override
     {
         copra_b200_constraint c{};
-        c.kind = COPRA_B200_CSTR_MIXED; c.rows = int(E_.rows()); c.is_ineq = isIneq_;
+        c.kind = COPRA_B200_CSTR_MIXED; c.rows = int(E_.rows()); c.is_ineq = isIneq_; c.full_size = fullSizeEntry_;
         c.E = b200::arr(E_.data()); c.G = b200::arr(G_.data()); c.f = b200::arr(f_.data());
         return c;
     }
@@ -610,13 +607,21 @@ public:
         else if (lower_.rows() == ps.fullXDim) { fullSizeEntry_ = true; nrConstr_ = lines; }
         else COPRA_DOMAIN_ERROR("lower / upper should have xDim or fullXDim rows");
         allocate(ps);
+        // The C ABI selects the finite lines itself.  After autoSpan() the reference keeps the line lists of the
+        // UN-spanned vectors (the re-selection at src/constraints.cpp:246-260 is dead code), so the vectors handed to
+        // the engine are masked to exactly lowerLines_ / upperLines_.
+        const double inf = std::numeric_limits<double>::infinity();
+        lowerSel_ = Eigen::VectorXd::Constant(lower_.rows(), -inf);
+        upperSel_ = Eigen::VectorXd::Constant(upper_.rows(), inf);
+        for (int l : lowerLines_) lowerSel_(l) = lower_(l);
+        for (int l : upperLines_) upperSel_(l) = upper_(l);
     }
     ConstraintFlag constraintType() const noexcept override { return ConstraintFlag::InequalityConstraint; }
     copra_b200_constraint describe() const override
     {
         copra_b200_constraint c{};
-        c.kind = COPRA_B200_CSTR_TRAJECTORY_BOUND; c.rows = int(lower_.rows()); c.is_ineq = 1;
-        c.lower = b200::arr(lower_.data()); c.upper = b200::arr(upper_.data());
+        c.kind = COPRA_B200_CSTR_TRAJECTORY_BOUND; c.rows = int(lower_.rows()); c.is_ineq = 1; c.full_size = fullSizeEntry_;
+        c.lower = b200::arr(lowerSel_.data()); c.upper = b200::arr(upperSel_.data());
         return c;
     }
 
@@ -633,7 +638,7 @@ private:
             for (int l = 0; l < upper_.rows(); ++l) if (upper_(l) != inf) upperLines_.push_back(l);
         }
     }
-    Eigen::VectorXd lower_, upper_;
+    Eigen::VectorXd lower_, upper_, lowerSel_, upperSel_;
     std::vector<int> lowerLines_, upperLines_;
 };
 
@@ -672,7 +677,7 @@ public:
     copra_b200_constraint describe() const override
     {
         copra_b200_constraint c{};
-        c.kind = COPRA_B200_CSTR_CONTROL_BOUND; c.rows = int(lower_.rows());
+        c.kind = COPRA_B200_CSTR_CONTROL_BOUND; c.rows = int(lower_.rows()); c.full_size = fullSizeEntry_;
         c.lower = b200::arr(lower_.data()); c.upper = b200::arr(upper_.data());
         return c;
     }
@@ -791,10 +796,6 @@ public:
         using clock = std::chrono::high_resolution_clock;
         const auto t0 = clock::now();
         if (!ps_->isUpdated) ps_->updateSystem(); // fills the public Phi/Psi/xi once, like :233-235
-        for (auto& c : spCost_)
-            if (c->fullSizeEntry()) COPRA_RUNTIME_ERROR("full-size (autoSpan'd) cost entries are not evaluated on the B200 path yet");
-        for (auto& c : constraints_.spConstr)
-            if (c->fullSizeEntry()) COPRA_RUNTIME_ERROR("full-size (autoSpan'd) constraint entries are not evaluated on the B200 path yet");
         b200::Description D;
         describe(D);
         copra_b200_handle* h = b200::handle();

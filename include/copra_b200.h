@@ -63,8 +63,11 @@ typedef struct {
 enum { COPRA_B200_COST_TRAJECTORY = 0, COPRA_B200_COST_TARGET = 1, COPRA_B200_COST_CONTROL = 2, COPRA_B200_COST_MIXED = 3 };
 typedef struct {
     int kind;
-    int rows;            /* rows of M / N / p / w (step-size entries: M rows x nx, N rows x nu) */
+    int rows;            /* rows of M / N / p / w */
     copra_b200_array M, N, p, w;
+    int full_size;       /* 0: step-size entry (M rows x nx, N rows x nu, applied at every step);
+                            1: full-size entry (M rows x nx(N+1), N rows x nu*N) -- the `fullSizeEntry_` branch of
+                               src/costFunctions.cpp:65-71,141-146,197-203; not allowed for TARGET (:95-97) */
 } copra_b200_cost;
 
 /* ---- constraints: reference include/constraints.h:114-307, src/constraints.cpp:45-367 ---- */
@@ -80,6 +83,8 @@ typedef struct {
     int rows;            /* rows of E/G/f, or entries of lower/upper */
     int is_ineq;         /* TRAJECTORY/CONTROL/MIXED only */
     copra_b200_array E, G, f, lower, upper;
+    int full_size;       /* 1: E rows x nx(N+1), G rows x nu*N, lower/upper with nx(N+1) (trajectory) or nu*N (control)
+                               entries -- src/constraints.cpp:68-73,122-126,199-204,297-299,346-351 */
 } copra_b200_constraint;
 
 /* ---- a batch of LMPC / InitialStateLMPC problems of ONE shape ----

@@ -520,6 +520,62 @@ static void initialStateComparison() // tests/TestLMPC_InitialState.cpp:29-260 (
     for (int i = 0; i < xDim; ++i) { REQUIRE_LE(xo(i), 1.0 + 1e-6); REQUIRE_LE(-1.0 - 1e-6, xo(i)); }
 }
 
+static void fullSizeEntriesSolve() // autoSpan'd (full-size) entries give the same controller as step-size entries
+{
+    IneqSystem s;
+    s.nbStep = 40;
+    auto ps = std::make_shared<copra::PreviewSystem>();
+    ps->system(s.A, s.B, s.c, s.x0, s.nbStep);
+    auto build = [&](copra::LMPC& ctl, bool span) {
+        auto xCost = std::make_shared<copra::TrajectoryCost>(s.M, s.xd);
+        auto uCost = std::make_shared<copra::ControlCost>(s.N, s.ud);
+        auto mCost = std::make_shared<copra::MixedCost>(Eigen::MatrixXd::Ones(1, 2), Eigen::MatrixXd::Ones(1, 1), Eigen::VectorXd::Ones(1));
+        auto trajConstr = std::make_shared<copra::TrajectoryConstraint>(s.E, s.p);
+        auto contConstr = std::make_shared<copra::ControlConstraint>(s.G, s.h);
+        auto mixConstr = std::make_shared<copra::MixedConstraint>(Eigen::MatrixXd::Ones(1, 2), Eigen::MatrixXd::Ones(1, 1), Eigen::VectorXd::Constant(1, 500.0));
+        auto bound = std::make_shared<copra::ControlBoundConstraint>(Eigen::VectorXd::Constant(1, -300.0), Eigen::VectorXd::Constant(1, 250.0));
+        xCost->weights(s.wx);
+        uCost->weights(s.wu);
+        mCost->weight(1e-3);
+        if (span) { xCost->autoSpan(); uCost->autoSpan(); mCost->autoSpan(); trajConstr->autoSpan(); contConstr->autoSpan(); mixConstr->autoSpan(); bound->autoSpan(); }
+        ctl.addCost(xCost); ctl.addCost(uCost); ctl.addCost(mCost);
+        ctl.addConstraint(trajConstr); ctl.addConstraint(contConstr); ctl.addConstraint(mixConstr); ctl.addConstraint(bound);
+        std::vector<std::shared_ptr<void>> keep = { xCost, uCost, mCost, trajConstr, contConstr, mixConstr, bound };
+        return keep;
+    };
+    copra::LMPC stepSize(ps), fullSize(ps);
+    auto k1 = build(stepSize, false);
+    auto k2 = build(fullSize, true);
+    // autoSpan() of step-size inputs leaves them step-size (max_dim == rows): span by hand to get real full-size entries
+    auto fM = std::make_shared<copra::TrajectoryCost>(spanMat(s.M, s.nbStep + 1), spanVec(s.xd, s.nbStep + 1));
+    fM->weights(s.wx);
+    auto fE = std::make_shared<copra::TrajectoryConstraint>(spanMat(s.E, s.nbStep + 1), spanVec(s.p, s.nbStep + 1));
+    auto fG = std::make_shared<copra::ControlConstraint>(spanMat(s.G, s.nbStep), spanVec(s.h, s.nbStep));
+    copra::LMPC dense(ps);
+    auto uCost = std::make_shared<copra::ControlCost>(spanMat(s.N, s.nbStep), spanVec(s.ud, s.nbStep));
+    uCost->weights(s.wu);
+    auto mCost = std::make_shared<copra::MixedCost>(spanMat(Eigen::MatrixXd::Ones(1, 2), s.nbStep, 1), spanMat(Eigen::MatrixXd::Ones(1, 1), s.nbStep), Eigen::VectorXd::Ones(s.nbStep));
+    mCost->weight(1e-3);
+    auto mixConstr = std::make_shared<copra::MixedConstraint>(spanMat(Eigen::MatrixXd::Ones(1, 2), s.nbStep, 1), spanMat(Eigen::MatrixXd::Ones(1, 1), s.nbStep), Eigen::VectorXd::Constant(s.nbStep, 500.0));
+    auto bound = std::make_shared<copra::ControlBoundConstraint>(Eigen::VectorXd::Constant(s.nbStep, -300.0), Eigen::VectorXd::Constant(s.nbStep, 250.0));
+    dense.addCost(fM); dense.addCost(uCost); dense.addCost(mCost);
+    dense.addConstraint(fE); dense.addConstraint(fG); dense.addConstraint(mixConstr); dense.addConstraint(bound);
+    REQUIRE(fM->fullSizeEntry() && fE->fullSizeEntry() && fG->fullSizeEntry() && mCost->fullSizeEntry() && bound->fullSizeEntry());
+    REQUIRE(stepSize.solve());
+    REQUIRE(fullSize.solve());
+    REQUIRE(dense.solve());
+    REQUIRE(stepSize.control().isApprox(fullSize.control(), 1e-9));
+    REQUIRE(stepSize.control().isApprox(dense.control(), 1e-7));
+    REQUIRE(stepSize.trajectory().isApprox(dense.trajectory(), 1e-7));
+    REQUIRE(stepSize.nrIneqConstr() == dense.nrIneqConstr());
+    const Eigen::MatrixXd &Qa = stepSize.Q(), &Qb = dense.Q();
+    bool same = true;
+    for (int j = 0; j < s.nbStep; ++j)
+        for (int i = 0; i < s.nbStep; ++i)
+            if (std::fabs(Qa(i, j) - Qb(i, j)) > 1e-10 * std::max(1.0, std::fabs(Qa(i, j)))) same = false;
+    REQUIRE(same);
+}
+
 static void batchedEntry()
 {
     BoundedSystem s;
@@ -595,6 +651,7 @@ int main(int argc, char** argv)
         groups.push_back({ "REMOVE_COST_AND_CONSTRAINT", removeAndDelete });
         groups.push_back({ "PLUGIN_PROTOCOL_AND_GETTERS", pluginProtocolAndGetters });
         groups.push_back({ "LMPC_AND_INITIAL-STATE-LMPC_COMPARISON", initialStateComparison });
+        groups.push_back({ "FULL_SIZE_ENTRIES_SOLVE", fullSizeEntriesSolve });
         groups.push_back({ "BATCHED_ENTRY", batchedEntry });
     }
     for (auto& g : groups) {

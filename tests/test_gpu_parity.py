@@ -260,3 +260,60 @@ def test_dgemm_dmma_primitive(engine):
         got = engine.dgemm(A, B, trans_a=ta)
         want = (np.swapaxes(A, 1, 2) if ta else A) @ B
         assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max()), (M, N, K, ta)
+
+
+def _span_m(M, steps, add_cols=0):
+    M = np.atleast_2d(np.asarray(M, float))
+    out = np.zeros((M.shape[0] * steps, M.shape[1] * (steps + add_cols)))
+    for i in range(steps):
+        out[i * M.shape[0]:(i + 1) * M.shape[0], i * M.shape[1]:(i + 1) * M.shape[1]] = M
+    return out
+
+
+@pytest.mark.parametrize("initial_state", [False, True])
+def test_full_size_entries_match_oracle(engine, initial_state):
+    """full-size (autoSpan'd) costs and constraints -- the dense `fullSizeEntry_` branches of the reference
+    (src/costFunctions.cpp:65-71,141-146,197-203; src/constraints.cpp:68-73,122-126,199-204,297-299,346-351) --
+    evaluated by the DMMA GEMM path, mixed with step-size entries, against the oracle"""
+    nx, nu, N = 2, 1, 9
+    rng = np.random.default_rng(5)
+    A = np.array([[1.0, 0.1], [0.0, 1.0]])
+    B = np.array([[0.005], [1.0]])
+    probs = []
+    for b in range(3):
+        M, Nm = np.eye(2), np.eye(1)
+        w_t = rng.uniform(0.5, 2.0, 2 * (N + 1))
+        prob = dict(nx=nx, nu=nu, N=N, initial_state=initial_state, A=A, B=B, d=np.array([0.01, -0.02]), x0=np.array([0.3, -1.0]) + 0.1 * b,
+                    costs=[dict(kind="trajectory", M=_span_m(M, N + 1), p=np.tile([0.1, 0.2], N + 1) + 0.01 * b, w=w_t),
+                           dict(kind="target", M=np.eye(2), p=np.ones(2), w=np.array([2.0, 3.0])),
+                           dict(kind="control", N=_span_m(Nm, N), p=np.full(N, 0.4), w=np.full(N, 0.1)),
+                           dict(kind="mixed", M=_span_m(np.ones((1, 2)), N, 1), N=_span_m(np.ones((1, 1)), N), p=np.full(N, 0.3), w=np.full(N, 0.3)),
+                           dict(kind="mixed", M=np.ones((1, 2)), N=np.ones((1, 1)), p=np.array([0.1]), w=np.array([0.2]))],
+                    constraints=[dict(kind="trajectory", E=_span_m(np.eye(2), N + 1), f=np.tile([50.0, 40.0], N + 1)),
+                                 dict(kind="control", G=_span_m(np.eye(1), N), f=np.full(N, 20.0)),
+                                 dict(kind="mixed", E=_span_m(np.array([[0.0, 1.0]]), N, 1), G=_span_m(np.array([[1.0]]), N), f=np.full(N, -0.5), is_ineq=False),
+                                 dict(kind="mixed", E=np.ones((1, 2)), G=np.ones((1, 1)), f=np.array([60.0])),
+                                 dict(kind="trajectory_bound", lower=np.full(nx * (N + 1), -np.inf), upper=np.tile([2.0, 1.0], N + 1)),
+                                 dict(kind="control_bound", lower=np.full(N, -1.0), upper=np.full(N, 1.5))])
+        if initial_state:
+            prob.update(R=np.array([[2.0, 0.1], [0.1, 1.0]]), r=np.array([0.1, -0.2]), x0lb=prob["x0"] - np.array([0.1, 0.5]),
+                        x0ub=prob["x0"] + np.array([0.1, 0.5]))
+        probs.append(prob)
+    # batch them (every array gets a leading batch axis)
+    def stack(key, sub=None, idx=None):
+        return np.stack([(p[key] if sub is None else p[sub][idx][key]) for p in probs])
+    bp = dict(name="full-size", nx=nx, nu=nu, N=N, batch=3, initial_state=initial_state, A=A, B=B, d=probs[0]["d"], x0=stack("x0"),
+              costs=[dict(c, p=stack("p", "costs", i), w=stack("w", "costs", i)) for i, c in enumerate(probs[0]["costs"])],
+              constraints=probs[0]["constraints"])
+    if initial_state:
+        bp.update(R=probs[0]["R"], r=probs[0]["r"], x0lb=stack("x0lb"), x0ub=stack("x0ub"))
+    hb = capi.HostBatch(bp)
+    out = engine.lmpc_run(hb)
+    stages = {k: engine.download(hb, k) for k in STAGES}
+    for i, prob in enumerate(probs):
+        o = po.lmpc(prob)
+        for k in STAGES:
+            assert rel_err(stages[k][i], o[k]) <= 1e-10, (k, i, rel_err(stages[k][i], o[k]))
+        assert out["status"][i] == o["fail"] == 0
+        assert x_err(out["x"][i], o["x"]) <= 1e-6
+        assert active_set(out["iact"][i], out["nact"][i]) == active_set(o["iact"])
