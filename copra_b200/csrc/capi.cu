@@ -795,9 +795,49 @@ int copra_b200_lmpc_run(copra_b200_handle* h, const copra_b200_problem* p, const
 {
     if (!h) return COPRA_B200_E_ARG;
     h->built = false;
-    int rc = do_build(h, p);
+    if (!p) return fail(h, COPRA_B200_E_ARG, "null problem");
+    const int kChunk = 32768;
+    if (p->batch <= 65535) {
+        int rc = do_build(h, p);
+        if (rc) return rc;
+        return do_solve(h, r);
+    }
+    // large batches: independent instances, so the batch is simply processed in chunks (the grid's y dimension
+    // and the workspace stay bounded); every (pointer, stride) pair and every result pointer is advanced
+    copra_b200_sizes sz;
+    int rc = copra_b200_lmpc_sizes(h, p, &sz);
     if (rc) return rc;
-    return do_solve(h, r);
+    auto adv = [](copra_b200_array a, long long b0) { if (a.ptr && a.stride) a.ptr += b0 * a.stride; return a; };
+    long long total_launches = 0;
+    for (long long b0 = 0; b0 < p->batch; b0 += kChunk) {
+        copra_b200_problem q = *p;
+        q.batch = int(std::min<long long>(kChunk, p->batch - b0));
+        q.A = adv(p->A, b0); q.B = adv(p->B, b0); q.d = adv(p->d, b0); q.x0 = adv(p->x0, b0);
+        q.R = adv(p->R, b0); q.r = adv(p->r, b0); q.x0lb = adv(p->x0lb, b0); q.x0ub = adv(p->x0ub, b0);
+        std::vector<copra_b200_cost> costs(p->costs, p->costs + p->ncost);
+        std::vector<copra_b200_constraint> cstrs(p->cstrs, p->cstrs + p->ncstr);
+        for (auto& c : costs) { c.M = adv(c.M, b0); c.N = adv(c.N, b0); c.p = adv(c.p, b0); c.w = adv(c.w, b0); }
+        for (auto& c : cstrs) { c.E = adv(c.E, b0); c.G = adv(c.G, b0); c.f = adv(c.f, b0); c.lower = adv(c.lower, b0); c.upper = adv(c.upper, b0); }
+        q.costs = costs.data();
+        q.cstrs = cstrs.data();
+        copra_b200_results rr{};
+        if (r) {
+            rr = *r;
+            if (r->control) rr.control = r->control + b0 * sz.nU;
+            if (r->trajectory) rr.trajectory = r->trajectory + b0 * sz.X;
+            if (r->x) rr.x = r->x + b0 * sz.nvar;
+            if (r->status) rr.status = r->status + b0;
+            if (r->iters) rr.iters = r->iters + 2 * b0;
+            if (r->nact) rr.nact = r->nact + b0;
+            if (r->iact) rr.iact = r->iact + b0 * sz.nvar;
+        }
+        if ((rc = do_build(h, &q))) return rc;
+        if ((rc = do_solve(h, r ? &rr : nullptr))) return rc;
+        total_launches += h->call_launches;
+    }
+    h->call_launches = total_launches;
+    h->built = false; // the workspace only holds the last chunk
+    return 0;
 }
 
 int copra_b200_lmpc_results(copra_b200_handle* h, const double* x, double* control, double* trajectory, int memory)

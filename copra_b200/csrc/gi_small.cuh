@@ -150,33 +150,41 @@ __device__ __forceinline__ void gs_rank1(double* __restrict__ M, int ld, int np,
     }
 }
 
-// Upper Cholesky in place + inverse of the factor, 128 threads, J column-major with leading dim ld.
-__device__ inline bool gs_factor(double* __restrict__ J, int ld, int n, int n2, double* __restrict__ row, double* __restrict__ rowk)
+// Upper Cholesky Q = R'R and J = R^-1, fused: step k of LINPACK dpofa (right-looking) and step k of dpori touch
+// disjoint entries (rows > k vs rows <= k of the columns j > k), so both are ONE rank-1 sweep
+//     J[i,j] = (i == k ? 0 : J[i,j]) + mult[j] * coef[i],   i <= j,  j > k
+// with mult[j] = R[k,j], coef[i] = -J[i,k]/R[k,k] (i < k), 1/R[k,k] (i == k), -R[k,i] (i > k).  Every entry sees
+// its updates in LINPACK's order; two block barriers per k.  128 threads, lane = row pair, warp = column group.
+__device__ inline bool gs_factor(double* __restrict__ J, int ld, int n, int n2, double* __restrict__ coef, double* __restrict__ mult)
 {
     const int tid = threadIdx.x, lane = lane_id(), g = tid >> 5;
-    // ---- R'R = Q (LINPACK dpofa result, right-looking) ----
     double akk = J[0];
     for (int k = 0; k < n; ++k) {
         if (!(akk > 0.0)) return false;
         const double rkk = sqrt(akk);
-        if (tid > k && tid < n) {
-            const double v = J[k + size_t(tid) * ld] / rkk;
-            J[k + size_t(tid) * ld] = v;
-            row[tid] = v;
+        const double inv = 1.0 / rkk;
+        if (tid < n2) {
+            double c;
+            if (tid < k) c = J[tid + size_t(k) * ld] * (-inv);
+            else if (tid == k) c = inv;
+            else if (tid < n) {
+                const double mj = J[k + size_t(tid) * ld] / rkk;
+                mult[tid] = mj;
+                c = -mj;
+            } else c = 0.0; // pad row of an odd n
+            coef[tid] = c;
         }
         __syncthreads();
-        if (tid == k) J[k + size_t(k) * ld] = rkk; // after the barrier: every thread holds akk in a register
-        // A[i,j] -= R[k,i] R[k,j] for k < i <= j: lane = row pair, warp = column group
+        if (tid <= k) J[tid + size_t(k) * ld] = coef[tid]; // column k of the inverse (dpori), diagonal = 1/R[k,k]
         {
             const int i0 = 2 * lane, i1 = i0 + 1;
-            if (i1 > k && i0 < n) {
-                const double r0 = (i0 > k) ? row[i0] : 0.0, r1 = (i1 < n) ? row[i1] : 0.0;
-                const int jstart = (i0 > k ? i0 : k + 1);
-                for (int j = jstart + ((g - jstart) & 3); j < n; j += 4) {
+            if (i0 < n) {
+                const double2 c = ld2(coef + i0);
+                for (int j = max(k + 1, i0) + ((g - max(k + 1, i0)) & 3); j < n; j += 4) {
                     double2 a = ld2(J + i0 + size_t(j) * ld);
-                    const double rj = row[j];
-                    a.x -= r0 * rj;
-                    if (i1 <= j) a.y -= r1 * rj;
+                    const double mj = mult[j];
+                    a.x = ((i0 == k) ? 0.0 : a.x) + mj * c.x;
+                    if (i1 <= j) a.y = ((i1 == k) ? 0.0 : a.y) + mj * c.y;
                     *reinterpret_cast<double2*>(J + i0 + size_t(j) * ld) = a;
                 }
             }
@@ -184,30 +192,7 @@ __device__ inline bool gs_factor(double* __restrict__ J, int ld, int n, int n2, 
         __syncthreads();
         if (k + 1 < n) akk = J[(k + 1) + size_t(k + 1) * ld];
     }
-    // ---- J = R^-1 in place (LINPACK dpori order) ----
-    for (int k = 0; k < n; ++k) {
-        const double inv = 1.0 / J[k + size_t(k) * ld];
-        if (tid < k) row[tid] = J[tid + size_t(k) * ld] * (-inv);
-        if (tid == k) { row[k] = inv; row[k + 1] = 0.0; }
-        if (tid > k && tid < n) rowk[tid] = J[k + size_t(tid) * ld];
-        __syncthreads();
-        if (tid <= k) J[tid + size_t(k) * ld] = row[tid];
-        {
-            const int i0 = 2 * lane;
-            if (i0 <= k) {
-                const double r0 = row[i0], r1 = row[i0 + 1]; // row[k+1] == 0 pads an odd tail
-                for (int j = k + 1 + g; j < n; j += 4) {
-                    const double t = rowk[j];
-                    double2 a = ld2(J + i0 + size_t(j) * ld);
-                    a.x = (i0 < k) ? a.x + t * r0 : t * r0;
-                    if (i0 + 1 <= k) a.y = (i0 + 1 < k) ? a.y + t * r1 : t * r1;
-                    *reinterpret_cast<double2*>(J + i0 + size_t(j) * ld) = a;
-                }
-            }
-        }
-        __syncthreads();
-    }
-    // strict lower triangle := 0 (qpgen2 label 21); pad row/column stay zero
+    // strict lower triangle := 0 (qpgen2 label 21); pad row/column are zeroed by the caller
     for (int idx = tid; idx < n2 * n2; idx += kSmT) {
         const int i = idx % n2, j = idx / n2;
         if (i > j) J[i + size_t(j) * ld] = 0.0;

@@ -317,3 +317,19 @@ def test_full_size_entries_match_oracle(engine, initial_state):
         assert out["status"][i] == o["fail"] == 0
         assert x_err(out["x"][i], o["x"]) <= 1e-6
         assert active_set(out["iact"][i], out["nact"][i]) == active_set(o["iact"])
+
+
+def test_batch_larger_than_grid_limit_is_chunked(engine):
+    """batches > 65535 instances are processed in chunks by copra_b200_lmpc_run; results equal the small-batch ones"""
+    base = wl.c2(batch=8, N=6)
+    reps = 8200  # 65600 instances
+    big = dict(base, batch=8 * reps)
+    for k in ("A", "B", "d", "x0"):
+        big[k] = np.tile(base[k], (reps,) + (1,) * (np.asarray(base[k]).ndim - 1))
+    big["costs"] = [dict(c, p=np.tile(c["p"], (reps, 1)) if np.asarray(c["p"]).ndim == 2 else c["p"]) for c in base["costs"]]
+    big["constraints"] = [dict(c, upper=np.tile(c["upper"], (reps, 1)) if np.asarray(c["upper"]).ndim == 2 else c["upper"])
+                          for c in base["constraints"]]
+    small = engine.lmpc_run(base)
+    out = engine.lmpc_run(big, want=("control", "status", "nact"))
+    assert (out["status"] == 0).all()
+    assert np.array_equal(out["control"].reshape(reps, 8, -1), np.broadcast_to(small["control"], (reps,) + small["control"].shape))
