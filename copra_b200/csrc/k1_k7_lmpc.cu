@@ -25,9 +25,8 @@ __device__ __forceinline__ double add_(double a, double b) { return __dadd_rn(a,
 // Phi_i = A Phi_{i-1}, G_k = A G_{k-1} (G_0 = B), xi_i = A xi_{i-1} + d.  Sequential in the step index,
 // parallel over the nx*nx + nx*nu + nx entries of one step and over instances.
 // ------------------------------------------------------------------------------------------------
-__global__ void k1_condense_kernel(const __grid_constant__ BuildParams P)
+__device__ __forceinline__ void dev_condense(const BuildParams& P, double* sm, int b)
 {
-    extern __shared__ double sm[];
     const int nx = P.nx, nu = P.nu, N = P.N, X = P.X;
     const int nA = nx * nx, nB = nx * nu, per = nA + nB + nx;
     double* sA = sm;            // nx x nx
@@ -35,7 +34,7 @@ __global__ void k1_condense_kernel(const __grid_constant__ BuildParams P)
     double* nxt = cur + per;
     double* sd = nxt + per;     // nx
     const long long NX = (long long)N * nx;
-    for (int b = blockIdx.x; b < P.batch; b += gridDim.x) {
+    {
         const double* A = P.A.at(b);
         const double* Bm = P.B.at(b);
         const double* d = P.d.at(b);
@@ -80,6 +79,12 @@ __global__ void k1_condense_kernel(const __grid_constant__ BuildParams P)
             double* tmp = cur; cur = nxt; nxt = tmp;
         }
     }
+}
+
+__global__ void k1_condense_kernel(const __grid_constant__ BuildParams P)
+{
+    extern __shared__ double sm[];
+    for (int b = blockIdx.x; b < P.batch; b += gridDim.x) dev_condense(P, sm, b);
 }
 
 int k1_condense_launch(const BuildParams& P, cudaStream_t st)
@@ -135,12 +140,12 @@ int k1_psi_fill_launch(const double* Gs, long long sGs, double* Psi, int nx, int
 // (reference: tmp = M_*Psi.block(..), M_*Phi.block(..), M_*xi.segment(..)-p_  src/costFunctions.cpp:74-78;
 //  E_*Psi.block, E_*Phi.block, f_-E_*xi.segment  src/constraints.cpp:77-81)
 // ------------------------------------------------------------------------------------------------
-__global__ void k2_precompute_kernel(const __grid_constant__ BuildParams P)
+__device__ __forceinline__ void dev_precompute(const BuildParams& P, int b)
 {
     const int nx = P.nx, nu = P.nu, N = P.N, X = P.X;
     const long long NX = (long long)N * nx;
     const int tid = threadIdx.x, T = blockDim.x;
-    for (int b = blockIdx.x; b < P.batch; b += gridDim.x) {
+    {
         const double* Phi = P.Phi + (long long)b * X * nx;
         const double* Gs = P.Gs + (long long)b * NX * nu;
         const double* xi = P.xi + (long long)b * X;
@@ -228,20 +233,21 @@ __global__ void k2_precompute_kernel(const __grid_constant__ BuildParams P)
     }
 }
 
+__global__ void k2_precompute_kernel(const __grid_constant__ BuildParams P)
+{
+    for (int b = blockIdx.x; b < P.batch; b += gridDim.x) dev_precompute(P, b);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K2b: Hessian block Q = 1e-6 I + sum_costs sum_i T_i' W T_i  (LMPC::updateSystem :228-229 +
 // makeQPForm :252-255 + cost update loops).  One thread per (block diagonal dd, a, b) chain walking
 // jmax = N-1 .. |dd|; Toeplitz => the entry at jmax is a running sum over kk = i - jmax ascending.
 // grid = (chain tiles, batch)
 // ------------------------------------------------------------------------------------------------
-__global__ void k2_assemble_q_kernel(const __grid_constant__ BuildParams P)
+__device__ __forceinline__ void dev_q_chain(const BuildParams& P, int b, int ch)
 {
     const int nu = P.nu, N = P.N, nvar = P.nvar;
     const int off = P.initial_state ? P.nx : 0;
-    const int b = blockIdx.y;
-    const int nchain = (2 * N - 1) * nu * nu;
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= nchain) return;
     const int a = ch % nu, bb = (ch / nu) % nu, dd = ch / (nu * nu) - (N - 1); // dd = j1 - j2
     const int ad = dd < 0 ? -dd : dd;
     double* Q = P.Q + (long long)b * nvar * nvar;
@@ -297,17 +303,21 @@ __global__ void k2_assemble_q_kernel(const __grid_constant__ BuildParams P)
     }
 }
 
+__global__ void k2_assemble_q_kernel(const __grid_constant__ BuildParams P)
+{
+    const int nchain = (2 * P.N - 1) * P.nu * P.nu;
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch < nchain) dev_q_chain(P, blockIdx.y, ch);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K2c: per-cost E (nx x nU) and f (nU):  E = sum_i MPhi_i' W T_i, f = sum_i res_i' W T_i
 // (src/costFunctions.cpp:77-78,105-106,210-211).  One thread per (s|f, column).  grid = (tiles, batch)
 // ------------------------------------------------------------------------------------------------
-__global__ void k2_assemble_ef_kernel(const __grid_constant__ BuildParams P)
+__device__ __forceinline__ void dev_ef(const BuildParams& P, int b, int t)
 {
     const int nx = P.nx, nu = P.nu, nU = P.nU;
-    const int b = blockIdx.y;
     const int per = (nx + 1) * nU;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= per * P.ncost) return;
     const int ci = t / per, rem = t % per;
     const int s = rem % (nx + 1), col = rem / (nx + 1);
     const int j = col / nu, bb = col % nu;
@@ -331,19 +341,22 @@ __global__ void k2_assemble_ef_kernel(const __grid_constant__ BuildParams P)
     else F.f[(long long)b * F.sf + col] = acc;
 }
 
+__global__ void k2_assemble_ef_kernel(const __grid_constant__ BuildParams P)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < (P.nx + 1) * P.nU * P.ncost) dev_ef(P, blockIdx.y, t);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K3: constraint rows.  A_i[:, block j] = EGx[i-j] (j <= i, j < N), zero otherwise
 // (src/constraints.cpp:77,142,209-219,289,302); in initial-state mode the first nx columns are Y
 // (src/InitialStateLMPC.cpp:88-101).  One thread per row, coalesced down each column.
 // grid = (row tiles over meq+mineq, batch)
 // ------------------------------------------------------------------------------------------------
-__global__ void k3_fill_rows_kernel(const __grid_constant__ BuildParams P)
+__device__ __forceinline__ void dev_fill_row(const BuildParams& P, int b, int row)
 {
     const int nx = P.nx, nu = P.nu, N = P.N, nvar = P.nvar;
     const int off = P.initial_state ? nx : 0;
-    const int b = blockIdx.y;
-    const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= P.meq + P.mineq) return;
     const bool iseq = row < P.meq;
     const int lrow = iseq ? row : row - P.meq;
     const int mtot = iseq ? P.meq : P.mineq;
@@ -371,6 +384,12 @@ __global__ void k3_fill_rows_kernel(const __grid_constant__ BuildParams P)
             Aout[lrow + (long long)(off + j * nu + bb) * mtot] = v;
         }
     }
+}
+
+__global__ void k3_fill_rows_kernel(const __grid_constant__ BuildParams P)
+{
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row < P.meq + P.mineq) dev_fill_row(P, blockIdx.y, row);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -455,12 +474,12 @@ __global__ void k3_gather_rows_kernel(const __grid_constant__ BuildParams P, int
 //  LMPC : c = sum_costs (E'x0 + f) ; b = z - Y x0             (src/costFunctions.cpp:81, constraints.cpp:82, LMPC.cpp:252-279)
 //  IS   : c = [r; sum f] ; Q_tr = sum E, Q_bl = Q_tr' ; b = z  (src/InitialStateLMPC.cpp:80-121)
 // ------------------------------------------------------------------------------------------------
-__global__ void k4_finalize_kernel(const __grid_constant__ BuildParams P)
+__device__ __forceinline__ void dev_finalize(const BuildParams& P, int b)
 {
     const int nx = P.nx, nu = P.nu, nU = P.nU, nvar = P.nvar;
     const int off = P.initial_state ? nx : 0;
     const int tid = threadIdx.x, T = blockDim.x;
-    for (int b = blockIdx.x; b < P.batch; b += gridDim.x) {
+    {
         const double* x0 = P.x0.at(b);
         double* c = P.c + (long long)b * nvar;
         double* Q = P.Q + (long long)b * nvar * nvar;
@@ -515,6 +534,11 @@ __global__ void k4_finalize_kernel(const __grid_constant__ BuildParams P)
             }
         }
     }
+}
+
+__global__ void k4_finalize_kernel(const __grid_constant__ BuildParams P)
+{
+    for (int b = blockIdx.x; b < P.batch; b += gridDim.x) dev_finalize(P, b);
 }
 
 // ------------------------------------------------------------------------------------------------
