@@ -65,7 +65,7 @@ EXPORTS = ["copra_b200_abi_version", "copra_b200_device_count", "copra_b200_crea
            "copra_b200_last_error", "copra_b200_set_stream", "copra_b200_synchronize", "copra_b200_launch_count",
            "copra_b200_last_timing", "copra_b200_condense", "copra_b200_solve_qp_batch", "copra_b200_lmpc_sizes",
            "copra_b200_lmpc_run", "copra_b200_lmpc_build", "copra_b200_lmpc_solve", "copra_b200_lmpc_download",
-           "copra_b200_lmpc_results", "copra_b200_dgemm_batch"]
+           "copra_b200_lmpc_results", "copra_b200_dgemm_batch", "copra_b200_lmpc_resolve", "copra_b200_fp64_peaks"]
 
 _lib = None
 
@@ -104,6 +104,8 @@ def load():
         lib.copra_b200_lmpc_solve.argtypes = [C.c_void_p, C.POINTER(Results)]
         lib.copra_b200_lmpc_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         lib.copra_b200_lmpc_results.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        lib.copra_b200_fp64_peaks.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        lib.copra_b200_lmpc_resolve.argtypes = [C.c_void_p, Array, C.c_int, C.POINTER(Results)]
         lib.copra_b200_dgemm_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int,
                                                C.c_longlong, C.c_void_p, C.c_int, C.c_longlong, C.c_double, C.c_void_p, C.c_int,
                                                C.c_longlong, C.c_int, C.c_int]
@@ -343,6 +345,28 @@ class Engine:
         self._check(self.lib.copra_b200_lmpc_run(self.h, C.byref(hb.problem), C.byref(r)))
         out["sizes"] = s
         return {k: v for k, v in out.items() if k in want or k == "sizes"}
+
+    def fp64_peaks(self):
+        """measured (DFMA, DMMA) TFLOP/s of this device"""
+        a, b = C.c_double(0), C.c_double(0)
+        self._check(self.lib.copra_b200_fp64_peaks(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def lmpc_resolve(self, x0, sizes):
+        """receding-horizon re-solve of the last built batch with new initial states x0 (batch, nx)"""
+        x0 = np.ascontiguousarray(np.asarray(x0, dtype=np.float64))
+        B = x0.shape[0]
+        out = dict(control=np.zeros((B, sizes["nU"])), trajectory=np.zeros((B, sizes["X"])), x=np.zeros((B, sizes["nvar"])),
+                   status=np.full(B, -1, np.int32), iters=np.zeros((B, 2), np.int32), nact=np.zeros(B, np.int32),
+                   iact=np.zeros((B, sizes["nvar"]), np.int32))
+        r = Results()
+        r.memory = HOST
+        for k, v in out.items():
+            setattr(r, k, v.ctypes.data)
+        a = Array()
+        a.ptr, a.stride = x0.ctypes.data, x0.shape[1]
+        self._check(self.lib.copra_b200_lmpc_resolve(self.h, a, HOST, C.byref(r)))
+        return out
 
     def lmpc_build(self, hb):
         self._check(self.lib.copra_b200_lmpc_build(self.h, C.byref(hb.problem)))

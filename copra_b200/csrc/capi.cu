@@ -59,6 +59,7 @@ struct copra_b200_handle {
     BuildParams bp{};
     Sizes sz;
     double vsmall = 0;
+    double fp64_peaks[2] = { 0.0, 0.0 }; // measured DFMA / DMMA TFLOP/s (lazy)
 };
 
 namespace {
@@ -853,6 +854,45 @@ int copra_b200_lmpc_run(copra_b200_handle* h, const copra_b200_problem* p, const
     h->call_launches = total_launches;
     h->built = false; // the workspace only holds the last chunk
     return 0;
+}
+
+int copra_b200_fp64_peaks(copra_b200_handle* h, double* dfma_tflops, double* dmma_tflops)
+{
+    if (!h || !dfma_tflops || !dmma_tflops) return COPRA_B200_E_ARG;
+    CU(cudaSetDevice(h->device));
+    if (h->fp64_peaks[0] <= 0.0) {
+        double* scratch = nullptr;
+        int rc = ws(h, "peak_scratch", 1, &scratch);
+        if (rc) return rc;
+        const int r = fp64_peaks_measure(h->sms, scratch, h->stream, &h->fp64_peaks[0], &h->fp64_peaks[1]);
+        if (r < 0) return fail(h, COPRA_B200_E_CUDA, "fp64_peaks: %s", cudaGetErrorString(cudaError_t(-r)));
+        h->launches += 8;
+    }
+    *dfma_tflops = h->fp64_peaks[0];
+    *dmma_tflops = h->fp64_peaks[1];
+    return 0;
+}
+
+int copra_b200_lmpc_resolve(copra_b200_handle* h, copra_b200_array x0, int memory, const copra_b200_results* r)
+{
+    if (!h) return COPRA_B200_E_ARG;
+    if (!h->built) return fail(h, COPRA_B200_E_STATE, "copra_b200_lmpc_resolve needs a previous build on this handle");
+    BuildParams& P = h->bp;
+    if (P.initial_state) return fail(h, COPRA_B200_E_UNSUPPORTED, "re-solve with new x0 is defined for LMPC mode only");
+    if (!x0.ptr) return fail(h, COPRA_B200_E_ARG, "x0 is required");
+    CU(cudaSetDevice(h->device));
+    h->call_launches = 0;
+    for (bool& v : h->ev_valid) v = false;
+    int rc = record(h, 0);
+    if (rc) return rc;
+    Upload U;
+    U.add(x0, P.nx, &P.x0);
+    if ((rc = run_upload(h, U, P.batch, memory, "params_x0"))) return rc; // its own buffer: the other parameters stay resident
+    if ((rc = record(h, 1))) return rc;
+    if ((rc = record(h, 2))) return rc;
+    LAUNCHED(k4_finalize_launch(P, h->sms, h->stream));
+    if ((rc = record(h, 3))) return rc;
+    return do_solve(h, r);
 }
 
 int copra_b200_lmpc_results(copra_b200_handle* h, const double* x, double* control, double* trajectory, int memory)

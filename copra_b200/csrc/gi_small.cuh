@@ -22,6 +22,7 @@ namespace cb {
 
 constexpr int kSmT = 128; // threads per instance
 constexpr int kSmMaxN = 64;
+constexpr int kSmMinB = 4; // resident CTAs per SM the register budget is set for (128 registers)
 
 __host__ __device__ inline int ld_vec2(int rows) // rows -> even leading dimension == 2 (mod 4)
 {
@@ -35,7 +36,7 @@ struct GsLayout {
     size_t oIact, oRowmap, oRedI, oActive, oSgn, bytes;                                     // bytes
 };
 
-__host__ __device__ inline GsLayout gs_layout(int n, int meq, int m)
+__host__ __device__ inline GsLayout gs_layout(int n, int meq, int m, bool s_smem = true, bool a_smem = true)
 {
     GsLayout L;
     L.n = n; L.n2 = (n + 1) & ~1; L.ld = ld_vec2(n); L.lds = odd_ld(n);
@@ -43,8 +44,8 @@ __host__ __device__ inline GsLayout gs_layout(int n, int meq, int m)
     size_t o = 0;
     auto take = [&](size_t cnt) { size_t at = o; o += (cnt + 1) & ~size_t(1); return at; };
     L.oJ = take(size_t(L.ld) * L.n2);
-    L.oS = take(size_t(L.lds) * n);
-    L.oA = take(L.mg > 0 ? size_t(L.lda) * L.n2 : 0);
+    L.oS = take(s_smem ? size_t(L.lds) * n : 0);
+    L.oA = take(L.mg > 0 && a_smem ? size_t(L.lda) * L.n2 : 0);
     L.oX = take(L.n2); L.oD = take(L.n2); L.oZ = take(L.n2); L.oW = take(L.n2); L.oV = take(L.n2);
     L.oR = take(L.n2); L.oU = take(L.n2 + 2); L.oBg = take(L.mg2); L.oNorm = take(L.mg2);
     L.oLb = take(L.n2); L.oUb = take(L.n2); L.oRow = take(L.n2 + 2); L.oRowk = take(L.n2);
@@ -87,7 +88,8 @@ __device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpre
 // out[c] = sum_k M[k + c*ld] * vec[k] over k in [0,n2): warp wq owns columns [16wq,16wq+16), two lanes
 // per column (k halves), result valid in lanes < 16.  vec is read with stride `vs` (1 for a vector in
 // shared memory, lda for a row of the cached constraint matrix).
-__device__ __forceinline__ double gs_col_dot(const double* __restrict__ M, int ld, int n2, const double* __restrict__ vec, int vs)
+template <bool VG> // VG: vec is a row of the un-padded global constraint matrix (n entries; entry n of an odd n does not exist)
+__device__ __forceinline__ double gs_col_dot(const double* __restrict__ M, int ld, int n, int n2, const double* __restrict__ vec, int vs)
 {
     const int lane = lane_id(), c = (warp_id() << 4) + (lane & 15), h = lane >> 4;
     const int kh = ((n2 >> 1) + 1) & ~1;
@@ -99,7 +101,7 @@ __device__ __forceinline__ double gs_col_dot(const double* __restrict__ M, int l
         for (int k = k0; k < k1; k += 2) {
             const double2 j = ld2(col + k);
             s0 += j.x * vec[size_t(k) * vs];
-            s1 += j.y * vec[size_t(k + 1) * vs];
+            s1 += j.y * ((VG && k + 1 >= n) ? 0.0 : vec[size_t(k + 1) * vs]);
         }
     }
     s0 += s1;
@@ -123,6 +125,35 @@ __device__ __forceinline__ void gs_rowpair_dot(const double* __restrict__ M, int
             const double vc = vec[c];
             z0 += j.x * vc;
             z1 += j.y * vc;
+        }
+    }
+    z0 += __shfl_xor_sync(0xffffffffu, z0, 8);
+    z1 += __shfl_xor_sync(0xffffffffu, z1, 8);
+    z0 += __shfl_xor_sync(0xffffffffu, z0, 16);
+    z1 += __shfl_xor_sync(0xffffffffu, z1, 16);
+}
+
+// the same product for a row pair of the stacked general rows [Aeq; Aineq] read from global memory (L2): for a
+// fixed column the 8 pairs of a warp are 16 consecutive doubles, so every request is one or two 128-byte lines
+__device__ __forceinline__ void gs_rowpair_dot_global(const GiView& P, int pair, bool valid, int n, const double* __restrict__ vec,
+    double& z0, double& z1)
+{
+    const int g = lane_id() >> 3;
+    z0 = 0.0; z1 = 0.0;
+    if (valid) {
+        const int i0 = 2 * pair, i1 = i0 + 1, meq = P.meq, m = P.m;
+        const double* p0 = (i0 < meq) ? P.Aeq + i0 : P.Aineq + (i0 - meq);
+        const int s0 = (i0 < meq) ? meq : m;
+        const bool has1 = i1 < meq + m;
+        const double* p1 = (i1 < meq) ? P.Aeq + i1 : P.Aineq + (has1 ? i1 - meq : 0);
+        const int s1 = (i1 < meq) ? meq : m;
+#pragma unroll 4
+        for (int c = g; c < n; c += 4) {
+            const double a0 = __ldg(p0 + size_t(c) * s0);
+            const double a1 = has1 ? __ldg(p1 + size_t(c) * s1) : 0.0;
+            const double vc = vec[c];
+            z0 += a0 * vc;
+            z1 += a1 * vc;
         }
     }
     z0 += __shfl_xor_sync(0xffffffffu, z0, 8);
@@ -202,14 +233,21 @@ __device__ inline bool gs_factor(double* __restrict__ J, int ld, int n, int n2, 
 }
 
 // All 128 threads call with identical arguments.  Returns the QuadProg fail code.
-__device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, const GiOut& O, double vsmall, int max_iter)
+// AG: the general constraint rows stay in global memory (L2) in the caller's layout instead of a padded copy in
+// shared memory; SG: S = R^-1 lives in a per-CTA global workspace `Sg` (odd_ld(n) * n doubles).  Both trade a
+// little L2 latency per iteration for 20 KB of shared memory each, i.e. for more resident instances per SM.
+template <bool AG, bool SG>
+__device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, double* __restrict__ Sg, const GiOut& O, double vsmall,
+    int max_iter)
 {
     const int n = L.n, n2 = L.n2, ld = L.ld, lds = L.lds, meq = P.meq, m = P.m, mg = L.mg, mg2 = L.mg2, lda = L.lda;
     const int q = mg + 2 * n, np = n2 >> 1, npa = mg2 >> 1;
     const int tid = threadIdx.x, lane = lane_id(), wq = warp_id();
     double* __restrict__ J = W.J;
-    double* __restrict__ S = W.S;
+    double* __restrict__ S = SG ? Sg : W.S;
     double* __restrict__ A = W.A;
+    // element (i, k) of the stacked general rows [Aeq; Aineq] straight from global memory (AG)
+    auto ag = [&](int i, int k) -> double { return (i < meq) ? __ldg(P.Aeq + i + size_t(k) * meq) : __ldg(P.Aineq + (i - meq) + size_t(k) * m); };
     double* redv = W.red;        // [0..4) arg-min values, [4..8) slack of the winner / dd, [8..12) zz, [12..16) za
     int* redi = W.redi;
 
@@ -219,15 +257,16 @@ __device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, co
         J[idx] = (i < n && j < n) ? P.Q[i + size_t(j) * n] : ((i == j && i < n2) ? 1.0 : 0.0);
     }
     if (mg > 0) {
-        for (int idx = tid; idx < lda * n2; idx += kSmT) {
-            const int i = idx % lda, k = idx / lda;
-            double v = 0.0;
-            if (k < n) {
-                if (i < meq) v = P.Aeq[i + size_t(k) * meq];
-                else if (i < mg) v = P.Aineq[(i - meq) + size_t(k) * m];
+        if (!AG)
+            for (int idx = tid; idx < lda * n2; idx += kSmT) {
+                const int i = idx % lda, k = idx / lda;
+                double v = 0.0;
+                if (k < n) {
+                    if (i < meq) v = P.Aeq[i + size_t(k) * meq];
+                    else if (i < mg) v = P.Aineq[(i - meq) + size_t(k) * m];
+                }
+                A[idx] = v;
             }
-            A[idx] = v;
-        }
         for (int i = tid; i < mg2; i += kSmT) W.bg[i] = (i < meq) ? P.beq[i] : (i < mg ? P.bineq[i - meq] : 0.0);
     }
     for (int i = tid; i < n2; i += kSmT) {
@@ -254,7 +293,7 @@ __device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, co
         }
         // unconstrained minimiser x = J (J' (-c))
         {
-            const double s = gs_col_dot(J, ld, n2, W.v, 1);
+            const double s = gs_col_dot<false>(J, ld, n, n2, W.v, 1);
             if (lane < 16 && (wq << 4) + lane < n2) W.d[(wq << 4) + lane] = s;
         }
         __syncthreads();
@@ -266,7 +305,7 @@ __device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, co
         // norms of the general rows
         for (int i = tid; i < mg; i += kSmT) {
             double s = 0.0;
-            for (int k = 0; k < n; ++k) { const double v = A[i + size_t(k) * lda]; s += v * v; }
+            for (int k = 0; k < n; ++k) { const double v = AG ? ag(i, k) : A[i + size_t(k) * lda]; s += v * v; }
             W.norm[i] = sqrt(s);
         }
         __syncthreads();
@@ -298,7 +337,8 @@ __device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, co
             for (int base = 0; base < npa; base += 32) { // general rows: products with x, row pairs
                 const int pair = base + (wq << 3) + (lane & 7);
                 double p0, p1;
-                gs_rowpair_dot(A, lda, pair, pair < npa, 0, n, W.x, p0, p1);
+                if (AG) gs_rowpair_dot_global(P, pair, pair < npa, n, W.x, p0, p1);
+                else gs_rowpair_dot(A, lda, pair, pair < npa, 0, n, W.x, p0, p1);
                 if (lane < 8 && pair < npa) {
                     const int i0 = 2 * pair, i1 = i0 + 1;
                     consider(i0, (i0 < meq) ? double(W.sgn[i0]) * (p0 - W.bg[i0]) : W.bg[i0] - p0);
@@ -332,12 +372,18 @@ __device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, co
             double asign = -1.0; // general row: a = asign * A[nvl,:] ; bound row: a = asign * e_bj
             if (nvl < meq) asign = double(W.sgn[nvl]);
             else if (nvl >= mg) { bj = nvl - mg; if (bj >= n) { bj -= n; asign = 1.0; } }
+            // row nvl of the general constraints: (pointer, element stride)
+            const double* arow = A + nvl;
+            int astr = lda;
+            if (AG && bj < 0) {
+                if (nvl < meq) { arow = P.Aeq + nvl; astr = meq; } else { arow = P.Aineq + (nvl - meq); astr = m; }
+            }
 
             for (;;) { // label 55
                 if (bj >= 0) {
                     if (tid < n2) W.d[tid] = (tid < n) ? asign * J[bj + size_t(tid) * ld] : 0.0;
                 } else {
-                    const double s = gs_col_dot(J, ld, n2, A + nvl, lda);
+                    const double s = gs_col_dot<AG>(J, ld, n, n2, arow, astr);
                     if (lane < 16 && (wq << 4) + lane < n2) W.d[(wq << 4) + lane] = asign * s;
                 }
                 __syncthreads();
@@ -352,7 +398,7 @@ __device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, co
                         zz = z0 * z0 + z1 * z1;
                         const int i0 = 2 * pair;
                         if (bj >= 0) za = (i0 == bj) ? asign * z0 : ((i0 + 1 == bj) ? asign * z1 : 0.0);
-                        else za = asign * (z0 * A[nvl + size_t(i0) * lda] + z1 * A[nvl + size_t(i0 + 1) * lda]);
+                        else za = asign * (z0 * arow[size_t(i0) * astr] + ((AG && i0 + 1 >= n) ? 0.0 : z1 * arow[size_t(i0 + 1) * astr]));
                     }
                 }
                 MinIdx tc; tc.v = 0.0; tc.i = -1;
@@ -435,7 +481,7 @@ __device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, co
                         double s;
                         if (bj >= 0) s = (asign < 0.0) ? W.ub[bj] - W.x[bj] : W.x[bj] - W.lb[bj];
                         else {
-                            double acc = (tid < n) ? A[nvl + size_t(tid) * lda] * W.x[tid] : 0.0;
+                            double acc = (tid < n) ? arow[size_t(tid) * astr] * W.x[tid] : 0.0;
 #pragma unroll
                             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
                             if (lane == 0) redv[wq] = acc;

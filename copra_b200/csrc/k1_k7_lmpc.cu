@@ -9,6 +9,7 @@
 // the SAME accumulation order as the reference (steps ascending), with un-fused multiply/add so the
 // condensed matrices agree with the CPU oracle to the last bit where the order is defined.
 #include "engine.cuh"
+#include "gi_small.cuh"
 #include "gi_solver.cuh"
 #include "launch.h"
 
@@ -586,6 +587,46 @@ __global__ void k4_schur_kernel(const __grid_constant__ BuildParams P, double* w
     }
 }
 
+// nU <= 64: the same Schur block with the fused Cholesky + inverse sweep of the small solver (gi_small.cuh:
+// one rank-1 sweep and two barriers per pivot).  128 threads per instance, 4 instances resident per SM.
+__global__ void __launch_bounds__(kSmT, 4) k4_schur_small_kernel(const __grid_constant__ BuildParams P)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int nx = P.nx, nU = P.nU, nvar = P.nvar, n2 = (nU + 1) & ~1, ld = ld_vec2(nU);
+    const int tid = threadIdx.x;
+    double* Jm = sm;                       // ld x n2
+    double* coef = Jm + (size_t)ld * n2;   // n2 + 2
+    double* mult = coef + n2 + 2;          // n2
+    double* V = mult + n2;                 // nx x nU
+    for (int b = blockIdx.x; b < P.batch; b += gridDim.x) {
+        double* Q = P.Q + (long long)b * nvar * nvar;
+        __syncthreads();
+        for (int idx = tid; idx < ld * n2; idx += kSmT) {
+            const int i = idx % ld, j = idx / ld;
+            Jm[idx] = (i < nU && j < nU) ? Q[(nx + i) + (long long)(nx + j) * nvar] : ((i == j && i < n2) ? 1.0 : 0.0);
+        }
+        __syncthreads();
+        const bool ok = gs_factor(Jm, ld, nU, n2, coef, mult);
+        if (ok) {
+            for (int t = tid; t < nx * nU; t += kSmT) { // V[s,i] = sum_{k<=i} E[s,k] J[k,i]
+                const int s = t % nx, i = t / nx;
+                double acc = 0.0;
+                for (int k = 0; k <= i; ++k) acc += Q[s + (long long)(nx + k) * nvar] * Jm[k + (size_t)i * ld];
+                V[t] = acc;
+            }
+            __syncthreads();
+        }
+        for (int t = tid; t < nx * nx; t += kSmT) {
+            const int s = t % nx, u = t / nx;
+            double acc = 0.0;
+            if (ok) for (int i = 0; i < nU; ++i) acc += V[s + (size_t)i * nx] * V[u + (size_t)i * nx];
+            else acc = CUDART_NAN; // Hessian not PD: the solver will report fail=2 on the NaN pivot
+            const double Rv = P.R.p ? P.R.at(b)[t] : 0.0;
+            Q[s + (long long)u * nvar] = Rv + acc;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K7: LMPC::updateResults (src/LMPC.cpp:282-286 / InitialStateLMPC.cpp:124-128):
 //   control = result (tail), trajectory = Phi x0 + Psi U + xi with Psi applied as the block-Toeplitz
@@ -703,7 +744,16 @@ int k2k4_assemble_launch(const BuildParams& P, double* schur_ws, long long schur
     }
     k4_finalize_kernel<<<pgrid, 128, 0, st>>>(P);
     CB_CHECK_LAUNCH();
-    if (P.initial_state) {
+    if (P.initial_state && P.nU <= kSmMaxN) {
+        const int n2 = (P.nU + 1) & ~1;
+        const size_t smem = sizeof(double) * (size_t(ld_vec2(P.nU)) * n2 + 2 * size_t(n2) + 2 + size_t(P.nx) * P.nU);
+        if (smem + 1024 > smem_optin) return -int(cudaErrorInvalidValue);
+        cudaError_t e = cudaFuncSetAttribute(k4_schur_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return -int(e);
+        const int per_sm = int(std::max<size_t>(1, std::min<size_t>(4, (smem_optin + 1024) / (smem + 1024))));
+        k4_schur_small_kernel<<<std::min(P.batch, sms * per_sm), kSmT, smem, st>>>(P);
+        CB_CHECK_LAUNCH();
+    } else if (P.initial_state) {
         const int ld = odd_ld(P.nU);
         size_t base = sizeof(double) * (2 * size_t(P.nU) + 1 + size_t(P.nx) * P.nU);
         size_t withJ = base + sizeof(double) * size_t(ld) * P.nU;
@@ -719,6 +769,13 @@ int k2k4_assemble_launch(const BuildParams& P, double* schur_ws, long long schur
         CB_CHECK_LAUNCH();
     }
     return launches;
+}
+
+int k4_finalize_launch(const BuildParams& P, int sms, cudaStream_t st)
+{
+    k4_finalize_kernel<<<std::min(P.batch, sms * 8), 128, 0, st>>>(P);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 1 : -int(e);
 }
 
 int k7_results_launch(const BuildParams& P, const double* x, double* control, double* trajectory, cudaStream_t st)

@@ -42,13 +42,16 @@ __global__ void __launch_bounds__(MAXT, MINB) gi_batch_kernel(const __grid_const
     }
 }
 
-// n <= 64: latency-optimised 128-thread variant (gi_small.cuh), everything resident in shared memory
-__global__ void __launch_bounds__(kSmT, 3) gi_small_kernel(const __grid_constant__ GiBatch B)
+// n <= 64: latency-optimised 128-thread variant (gi_small.cuh).  J always lives in shared memory; the variants
+// differ in where S = R^-1 and the general constraint rows live (shared memory, or global/L2) and therefore in
+// how many instances are resident per SM (kSmMinB = 4 CTAs per SM sets the register budget: 128).
+template <bool AG, bool SG> __global__ void __launch_bounds__(kSmT, kSmMinB) gi_small_kernel(const __grid_constant__ GiBatch B)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_next;
-    const GsLayout L = gs_layout(B.n, B.meq, B.m);
+    const GsLayout L = gs_layout(B.n, B.meq, B.m, !SG, !AG);
     GsWork W = gs_carve(L, smem);
+    double* Sg = SG ? B.ws + (long long)blockIdx.x * B.ws_stride : nullptr;
     for (;;) {
         if (threadIdx.x == 0) s_next = atomicAdd(B.counter, 1);
         __syncthreads();
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(kSmT, 3) gi_small_kernel(const __grid_constant
         O.iters = B.iters ? B.iters + 2LL * b : nullptr;
         O.nact = B.nact ? B.nact + b : nullptr;
         O.iact = B.iact ? B.iact + (long long)b * B.n : nullptr;
-        gs_solve(P, L, W, O, B.vsmall, B.max_iter);
+        gs_solve<AG, SG>(P, L, W, Sg, O, B.vsmall, B.max_iter);
         __syncthreads();
     }
 }
@@ -136,15 +139,33 @@ GiPlan gi_plan(int n, int meq, int m, int batch, int sms, size_t smem_optin)
     p.small = 0;
     p.cluster = 0;
     if (n <= kSmMaxN) {
-        const size_t b = gs_layout(n, meq, m).bytes;
-        if (b + 2048 <= smem_optin) {
+        // Residency variants, in order of preference: J,S,A in shared memory; S in global (L2); S and A in global.
+        // Measured on C2/C4 (profiles/r01_summary.md): 4 resident CTAs per SM at <= 128 registers is the sweet spot --
+        // fewer CTAs leave issue slots idle, more cost registers -- so take the first variant that reaches 4 per SM,
+        // else the one with the most.
+        int best = -1, best_per_sm = 0;
+        size_t best_bytes = 0;
+        for (int v = 0; v < 3; ++v) {
+            const size_t b = gs_layout(n, meq, m, v < 1, v < 2).bytes;
+            if (b + 2048 > smem_optin) continue;
+            const int per_sm = int(std::min<size_t>(kSmMinB, (smem_optin + 1024) / (b + 1024)));
+            if (per_sm > best_per_sm) { best = v; best_per_sm = per_sm; best_bytes = b; }
+            if (per_sm >= kSmMinB) break;
+        }
+        if (const char* e = getenv("COPRA_B200_SMALL_VARIANT")) { // tuning knob: force a residency variant
+            const int v = atoi(e);
+            if (v >= 0 && v < 3) {
+                const size_t b = gs_layout(n, meq, m, v < 1, v < 2).bytes;
+                if (b + 2048 <= smem_optin) { best = v; best_bytes = b; best_per_sm = int(std::min<size_t>(kSmMinB, (smem_optin + 1024) / (b + 1024))); }
+            }
+        }
+        if (best >= 0) {
             p.small = 1;
             p.threads = kSmT;
-            p.j_smem = p.s_smem = p.a_smem = 1;
-            p.smem_bytes = b;
-            p.ws_stride = 0;
-            const int per_sm = int(std::max<size_t>(1, std::min<size_t>(12, (smem_optin + 1024) / (b + 1024))));
-            p.grid = std::max(1, std::min(batch, sms * per_sm));
+            p.j_smem = 1; p.s_smem = best < 1; p.a_smem = best < 2;
+            p.smem_bytes = best_bytes;
+            p.ws_stride = p.s_smem ? 0 : (long long)odd_ld(n) * n;
+            p.grid = std::max(1, std::min(batch, sms * best_per_sm));
             return p;
         }
     }
@@ -194,6 +215,14 @@ template <int MAXT, int MINB> static cudaError_t gi_launch_t(const GiBatch& B, c
     return cudaGetLastError();
 }
 
+template <bool AG, bool SG> static cudaError_t gi_small_launch_t(const GiBatch& B, const GiPlan& plan, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(gi_small_kernel<AG, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes));
+    if (e != cudaSuccess) return e;
+    gi_small_kernel<AG, SG><<<plan.grid, plan.threads, plan.smem_bytes, st>>>(B);
+    return cudaGetLastError();
+}
+
 cudaError_t gi_cluster_launch(const GiBatch& B, const GiPlan& plan, double* Sws, int nclusters, cudaStream_t st)
 {
     cudaError_t e;
@@ -238,10 +267,9 @@ int gi_cluster_max_clusters(const GiPlan& plan)
 cudaError_t gi_launch(const GiBatch& B, const GiPlan& plan, cudaStream_t st)
 {
     if (plan.small) {
-        cudaError_t e = cudaFuncSetAttribute(gi_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes));
-        if (e != cudaSuccess) return e;
-        gi_small_kernel<<<plan.grid, plan.threads, plan.smem_bytes, st>>>(B);
-        return cudaGetLastError();
+        if (plan.s_smem) return gi_small_launch_t<false, false>(B, plan, st);
+        if (plan.a_smem) return gi_small_launch_t<false, true>(B, plan, st);
+        return gi_small_launch_t<true, true>(B, plan, st);
     }
     // register budgets: 128 thr x 6 CTA/SM, 256 thr x 3 CTA/SM (<= 80 regs), 512 thr x 1 (<= 128 regs)
     if (plan.threads <= 128) return gi_launch_t<128, 6>(B, plan, st);

@@ -46,6 +46,9 @@ int k2k4_assemble_launch(const BuildParams& P, double* schur_ws, long long schur
 // batched FP64 tensor-core GEMM (dgemm_dmma.cu): C = alpha op(A) B + beta C, column-major; returns launches or -cudaError
 int dgemm_dmma_launch(int transA, int M, int N, int K, double alpha, const double* A, int lda, long long sA, const double* B, int ldb,
     long long sB, double beta, double* C, int ldc, long long sC, int batch, cudaStream_t st);
+// measured DFMA / DMMA ceilings (fp64_peak.cu); 0 or -cudaError
+int fp64_peaks_measure(int sms, double* scratch, cudaStream_t st, double* dfma_tflops, double* dmma_tflops);
+int k4_finalize_launch(const BuildParams& P, int sms, cudaStream_t st);
 int k7_results_launch(const BuildParams& P, const double* x, double* control, double* trajectory, cudaStream_t st);
 
 } // namespace cb

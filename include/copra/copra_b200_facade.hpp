@@ -1046,7 +1046,27 @@ public:
         R.control = controls_.data(); R.trajectory = trajectories_.data(); R.status = status_.data(); R.iters = iterations_.data();
         R.nact = nact_.data(); R.iact = iact_.data(); R.memory = COPRA_B200_HOST;
         b200::check(copra_b200_lmpc_run(b200::handle(), finish(), &R));
-        ++b200::buildEpoch();
+        myEpoch_ = ++b200::buildEpoch();
+        copra_b200_timing tm{};
+        copra_b200_last_timing(b200::handle(), &tm);
+        solveTime_ = tm.solve_ms * 1e-3;
+        solveAndBuildTime_ = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+        return int(std::count(status_.begin(), status_.end(), 0));
+    }
+    // Receding-horizon step (reference usage: PreviewSystem::xInit + solve with isUpdated still set): only the initial
+    // states change; condensing, Q and the constraint matrices stay resident on the device.  LMPC mode only.
+    int resolve(copra_b200_array x0)
+    {
+        if (myEpoch_ != b200::buildEpoch()) { // another controller used the process-wide engine since: full rebuild
+            p_.x0 = x0;
+            return solve();
+        }
+        const auto t0 = std::chrono::high_resolution_clock::now();
+        copra_b200_results R{};
+        R.control = controls_.data(); R.trajectory = trajectories_.data(); R.status = status_.data(); R.iters = iterations_.data();
+        R.nact = nact_.data(); R.iact = iact_.data(); R.memory = COPRA_B200_HOST;
+        b200::check(copra_b200_lmpc_resolve(b200::handle(), x0, p_.memory, &R));
+        p_.x0 = x0;
         copra_b200_timing tm{};
         copra_b200_last_timing(b200::handle(), &tm);
         solveTime_ = tm.solve_ms * 1e-3;
@@ -1075,6 +1095,7 @@ private:
     std::vector<double> controls_, trajectories_;
     std::vector<int> status_, iterations_, nact_, iact_;
     double solveTime_ = 0, solveAndBuildTime_ = 0;
+    unsigned long myEpoch_ = ~0ul;
 };
 
 } // namespace copra

@@ -191,6 +191,14 @@ int copra_b200_lmpc_run(copra_b200_handle* h, const copra_b200_problem* p, const
 /* staged variants: build = K1..K5 (LMPC::updateSystem + makeQPForm), solve = K6+K7 */
 int copra_b200_lmpc_build(copra_b200_handle* h, const copra_b200_problem* p);
 int copra_b200_lmpc_solve(copra_b200_handle* h, const copra_b200_results* r);
+/* Measured FP64 ceilings of this device in TFLOP/s: a DFMA-chain and a DMMA.8x8x4-chain microbenchmark (the
+ * denominators of the FP64 roofline in bench.py).  Takes a few milliseconds; cached per handle. */
+int copra_b200_fp64_peaks(copra_b200_handle* h, double* dfma_tflops, double* dmma_tflops);
+/* Receding-horizon re-solve: only the initial states changed since the last build
+ * (PreviewSystem::xInit, include/PreviewSystem.h:52-54, leaves `isUpdated` set so the reference skips
+ * updateSystem's condensing too).  Re-runs K4 (c = E'x0 + f, b = z - Y x0) on the resident Phi/Gs/E/f/Y/z and
+ * K5..K7; Q, Aeq, Aineq are reused.  LMPC mode only (in initial-state mode x0 is a decision variable). */
+int copra_b200_lmpc_resolve(copra_b200_handle* h, copra_b200_array x0, int memory, const copra_b200_results* r);
 /* K7 alone -- LMPC::updateResults (src/LMPC.cpp:282-286) for an externally solved QP: `x` holds nvar doubles per
  * instance (the SI_result() of any SolverInterface); control / trajectory as in copra_b200_results. */
 int copra_b200_lmpc_results(copra_b200_handle* h, const double* x, double* control, double* trajectory, int memory);

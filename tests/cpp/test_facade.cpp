@@ -629,6 +629,18 @@ static void batchedEntry()
     for (int i = 0; i < N; ++i) if (ctl.controls()[size_t(7) * N + i] != one.control()(i)) same = false;
     REQUIRE(same); // instances are independent: bit-identical to the batch-of-one result
     REQUIRE(ctl.solveAndBuildTime() > 0 && ctl.solveTime() > 0);
+    // receding-horizon step: new initial states on the resident build == a fresh controller with those states
+    std::vector<double> x1(x0);
+    for (int b = 0; b < batch; ++b) x1[2 * b + 1] += 0.25;
+    REQUIRE(ctl.solve() == batch);                                  // the engine holds this batch again ...
+    REQUIRE(ctl.resolve(copra::b200::arr(x1.data(), 2)) == batch); // ... so this is the K4 + K5..K7 path
+    REQUIRE(ctl.solveTime() > 0);
+    x07 << x1[14], x1[15];
+    ps->xInit(x07);
+    REQUIRE(one.solve());
+    same = true;
+    for (int i = 0; i < N; ++i) if (ctl.controls()[size_t(7) * N + i] != one.control()(i)) same = false;
+    REQUIRE(same);
 }
 
 int main(int argc, char** argv)

@@ -333,3 +333,59 @@ def test_batch_larger_than_grid_limit_is_chunked(engine):
     out = engine.lmpc_run(big, want=("control", "status", "nact"))
     assert (out["status"] == 0).all()
     assert np.array_equal(out["control"].reshape(reps, 8, -1), np.broadcast_to(small["control"], (reps,) + small["control"].shape))
+
+
+def test_receding_horizon_resolve(engine):
+    """new x0 on a resident build (K4 + K5..K7 only) equals a full run with that x0, bit for bit"""
+    bp = wl.c2(batch=64)
+    first = engine.lmpc_run(bp)
+    x0_new = np.array(bp["x0"]) + np.array([0.0, 0.3])
+    again = engine.lmpc_resolve(x0_new, first["sizes"])
+    full = engine.lmpc_run(dict(bp, x0=x0_new))
+    assert (again["status"] == 0).all()
+    assert np.array_equal(again["control"], full["control"]) and np.array_equal(again["iact"], full["iact"])
+    assert np.array_equal(again["trajectory"], full["trajectory"])
+    assert not np.array_equal(again["control"], first["control"])
+
+
+def test_small_solver_residency_variants(engine, monkeypatch):
+    """gi_small_kernel keeps S and the general rows in shared memory or in global memory (L2) depending on how many
+    instances fit an SM; every variant runs the same algorithm (same pivots, same active sets; the compiler may
+    contract a*b+c*d differently per instantiation, so x agrees to rounding, not bit for bit)"""
+    rng = np.random.default_rng(11)
+    cases = []
+    for n, meq, m in ((7, 2, 9), (24, 3, 31), (51, 5, 60), (64, 0, 33)):
+        B = 6
+        L = rng.normal(size=(B, n, n))
+        Q = L @ np.swapaxes(L, 1, 2) + 0.1 * np.eye(n)
+        c = rng.normal(size=(B, n))
+        Aeq = rng.normal(size=(B, meq, n))
+        xf = rng.normal(size=(B, n))
+        beq = np.einsum("bij,bj->bi", Aeq, xf)
+        Aineq = rng.normal(size=(B, m, n))
+        bineq = np.einsum("bij,bj->bi", Aineq, xf) + rng.uniform(0.0, 1.0, size=(B, m))
+        lb = xf - rng.uniform(0.1, 2.0, size=(B, n))
+        ub = xf + rng.uniform(0.1, 2.0, size=(B, n))
+        cases.append((Q, c, Aeq if meq else None, beq if meq else None, Aineq, bineq, lb, ub))
+    bp = wl.c2(batch=48)
+    ref = None
+    for v in ("0", "1", "2"):
+        monkeypatch.setenv("COPRA_B200_SMALL_VARIANT", v)
+        out = [engine.solve_qp_batch(*cs) for cs in cases]
+        mpc = engine.lmpc_run(bp)
+        if ref is None:
+            ref = (out, mpc)
+            for cs, r in zip(cases, out):  # variant 0 against the oracle
+                for b in range(cs[0].shape[0]):
+                    o = po.quadprog(cs[0][b], cs[1][b], None if cs[2] is None else cs[2][b], None if cs[3] is None else cs[3][b],
+                                    cs[4][b], cs[5][b], cs[6][b], cs[7][b])
+                    assert r["status"][b] == o["fail"]
+                    if o["fail"] == 0:
+                        assert x_err(r["x"][b], o["x"]) < 1e-8
+                        assert tuple(r["iters"][b]) == o["iter"]
+            continue
+        for r0, r1 in zip(ref[0], out):
+            assert np.array_equal(r0["status"], r1["status"]) and np.array_equal(r0["iact"], r1["iact"])
+            assert np.array_equal(r0["iters"], r1["iters"])
+            assert np.allclose(r0["x"], r1["x"], rtol=1e-10, atol=1e-12)
+        assert np.allclose(ref[1]["control"], mpc["control"], rtol=1e-9, atol=1e-9) and np.array_equal(ref[1]["iact"], mpc["iact"])
