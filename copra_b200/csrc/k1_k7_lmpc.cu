@@ -26,6 +26,20 @@ __device__ __forceinline__ double add_(double a, double b) { return __dadd_rn(a,
 // Phi_i = A Phi_{i-1}, G_k = A G_{k-1} (G_0 = B), xi_i = A xi_{i-1} + d.  Sequential in the step index,
 // parallel over the nx*nx + nx*nu + nx entries of one step and over instances.
 // ------------------------------------------------------------------------------------------------
+// A read-only table that is either a slice of the CTA's dynamic shared memory (32-bit offsets, LDS) or a global array.
+extern __shared__ double stage_sm[];
+template <bool STAGED> struct Tab {
+    const double* g;
+    int o;
+    __device__ __forceinline__ double operator[](int i) const { return STAGED ? stage_sm[o + i] : g[i]; }
+    __device__ __forceinline__ Tab shifted(int d) const { return Tab{ g + d, o + d }; }
+};
+// cooperative copy of `count` doubles into stage_sm at offset `o`
+__device__ __forceinline__ void stage_copy(int o, const double* src, int count)
+{
+    for (int t = threadIdx.x; t < count; t += blockDim.x) stage_sm[o + t] = src[t];
+}
+
 __device__ __forceinline__ void dev_condense(const BuildParams& P, double* sm, int b)
 {
     const int nx = P.nx, nu = P.nu, N = P.N, X = P.X;
@@ -88,9 +102,80 @@ __global__ void k1_condense_kernel(const __grid_constant__ BuildParams P)
     for (int b = blockIdx.x; b < P.batch; b += gridDim.x) dev_condense(P, sm, b);
 }
 
+// Small systems (nx^2 + nx nu + nx <= 32): a sub-warp group of G = 8/16/32 lanes per instance, so that a 128-thread
+// CTA carries 128/G instances and the N-step power chain synchronises with __syncwarp instead of a block barrier --
+// the whole batch is one wave of short latency chains instead of several CTA-per-instance rounds.
+__global__ void __launch_bounds__(128) k1_condense_group_kernel(const __grid_constant__ BuildParams P, int G)
+{
+    extern __shared__ double sm[];
+    const int nx = P.nx, nu = P.nu, N = P.N, X = P.X;
+    const int nA = nx * nx, nB = nx * nu, per = nA + nB + nx;
+    const int grp = threadIdx.x / G, t = threadIdx.x % G, ngrp = blockDim.x / G;
+    const int stride = nA + 2 * per + nx;
+    double* sA = sm + grp * stride;
+    double* cur = sA + nA;
+    double* nxt = cur + per;
+    double* sd = nxt + per;
+    const long long NX = (long long)N * nx;
+    const int b = blockIdx.x * ngrp + grp;
+    if (b >= P.batch) return; // whole groups leave together; warps of mixed groups keep using __syncwarp on the rest
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~unsigned(G - 1)));
+    const double* A = P.A.at(b);
+    const double* Bm = P.B.at(b);
+    const double* d = P.d.at(b);
+    double* Phi = P.Phi + (long long)b * X * nx;
+    double* Gs = P.Gs + (long long)b * NX * nu;
+    double* xi = P.xi + (long long)b * X;
+    int r, c, kind; // this lane's entry of [Phi | G | xi]
+    if (t < nA) { kind = 0; r = t % nx; c = t / nx; }
+    else if (t < nA + nB) { kind = 1; r = (t - nA) % nx; c = (t - nA) / nx; }
+    else { kind = 2; r = t - nA - nB; c = 0; }
+    if (t < per) {
+        if (kind == 0) {
+            const double a = A[t];
+            sA[t] = a; cur[t] = a;
+            Phi[r + (long long)c * X] = (r == c) ? 1.0 : 0.0;
+            Phi[nx + r + (long long)c * X] = a;
+        } else if (kind == 1) {
+            const double v = Bm[t - nA];
+            cur[t] = v;
+            Gs[r + (long long)c * NX] = v;
+        } else {
+            const double v = d[r];
+            sd[r] = v; cur[t] = v;
+            xi[r] = 0.0;
+            xi[nx + r] = v;
+        }
+    }
+    __syncwarp(gmask);
+    const int srcoff = (kind == 0) ? c * nx : ((kind == 1) ? nA + c * nx : nA + nB);
+    for (int i = 2; i <= N; ++i) {
+        if (t < per) {
+            const double* src = cur + srcoff;
+            double s = 0.0;
+            for (int k = 0; k < nx; ++k) s = add_(s, mul_(sA[r + k * nx], src[k]));
+            if (kind == 0) Phi[(long long)i * nx + r + (long long)c * X] = s;
+            else if (kind == 1) Gs[(long long)(i - 1) * nx + r + (long long)c * NX] = s;
+            else { s = add_(s, sd[r]); xi[(long long)i * nx + r] = s; }
+            nxt[t] = s;
+        }
+        __syncwarp(gmask);
+        double* tmp = cur; cur = nxt; nxt = tmp;
+    }
+}
+
 int k1_condense_launch(const BuildParams& P, cudaStream_t st)
 {
     const int per = P.nx * P.nx + P.nx * P.nu + P.nx;
+    if (per <= 32) {
+        const int G = per <= 8 ? 8 : (per <= 16 ? 16 : 32);
+        const int ngrp = 128 / G;
+        const size_t smem = sizeof(double) * size_t(P.nx * P.nx + 2 * per + P.nx) * ngrp;
+        k1_condense_group_kernel<<<(P.batch + ngrp - 1) / ngrp, 128, smem, st>>>(P, G);
+        cudaError_t e = cudaGetLastError();
+        return e == cudaSuccess ? 1 : -int(e);
+    }
     const size_t smem = sizeof(double) * size_t(P.nx * P.nx + 2 * per + P.nx);
     int threads = std::min(256, ((per + 31) / 32) * 32);
     int grid = std::min(P.batch, 148 * 8);
@@ -245,7 +330,10 @@ __global__ void k2_precompute_kernel(const __grid_constant__ BuildParams P)
 // jmax = N-1 .. |dd|; Toeplitz => the entry at jmax is a running sum over kk = i - jmax ascending.
 // grid = (chain tiles, batch)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void dev_q_chain(const BuildParams& P, int b, int ch)
+// `qtile` != null: the chain writes into a dense nU x nU tile in shared memory (written out coalesced by the caller)
+// instead of walking a diagonal of Q in global memory with one 32-byte sector per 8-byte store.
+__device__ __forceinline__ void dev_q_chain(const BuildParams& P, int b, int ch, const double* const* MG, const double* const* Wt,
+    double* qtile)
 {
     const int nu = P.nu, N = P.N, nvar = P.nvar;
     const int off = P.initial_state ? P.nx : 0;
@@ -254,98 +342,214 @@ __device__ __forceinline__ void dev_q_chain(const BuildParams& P, int b, int ch)
     double* Q = P.Q + (long long)b * nvar * nvar;
     double run[kMaxCost];
     int done[kMaxCost];
-    const double* MG[kMaxCost];
-    const double* Wt[kMaxCost];
     for (int ci = 0; ci < P.ncost; ++ci) {
         run[ci] = 0.0;
         done[ci] = 0;
-        MG[ci] = P.cost[ci].MGx + (long long)b * P.cost[ci].sMGx;
-        Wt[ci] = P.cost[ci].w.at(b);
     }
-    for (int jmax = N - 1; jmax >= ad; --jmax) {
-        const int j1 = dd >= 0 ? jmax : jmax + dd;
-        const int j2 = j1 - dd;
+    // weighted dot of two r-vectors in the reference order: sum_l (ga[l] * w[l]) * gb[l]
+    auto wdot = [](const double* ga, const double* w, const double* gb, int r) {
+        double s = 0.0;
+        for (int l = 0; l < r; ++l) s = add_(s, mul_(mul_(ga[l], w[l]), gb[l]));
+        return s;
+    };
+    const int o1 = dd >= 0 ? 0 : -dd, o2 = dd >= 0 ? dd : 0; // jmax - j1, jmax - j2 (constant along the chain)
+    double* qout = qtile ? qtile + ((N - 1 - o1) * nu + a) + (long long)((N - 1 - o2) * nu + bb) * P.nU
+                         : Q + (off + (N - 1 - o1) * nu + a) + (long long)(off + (N - 1 - o2) * nu + bb) * nvar;
+    const long long qstep = (long long)nu * ((qtile ? P.nU : nvar) + 1); // one block up the diagonal per step
+    for (int jmax = N - 1; jmax >= ad; --jmax, qout -= qstep) {
         double val = (dd == 0 && a == bb) ? P.qdiag : 0.0;
         for (int ci = 0; ci < P.ncost; ++ci) {
             const CostFam& F = P.cost[ci];
             if (F.dense) continue; // added afterwards by the GEMM path (Q += T'WT)
-            const int r = F.rows;
+            const int r = F.rows, rnu = r * nu;
             // steps i in [max(i0,jmax), i1-1]  <->  kk = i - jmax
             const int kk_hi = F.i1 - 1 - jmax;
             if (kk_hi < 0) continue;
+            const double* base_a = MG[ci] + r * (a + nu * o1);
+            const double* base_b = MG[ci] + r * (bb + nu * o2);
             double contrib;
             if (F.i0 == 0) {
                 // running sum over kk ascending; terms are independent of jmax (Toeplitz), so only
                 // the not-yet-included kk in (done, kk_hi] are added at this jmax
-                const int o1 = jmax - j1, o2 = jmax - j2;
-                for (int kk = done[ci]; kk <= kk_hi; ++kk) {
-                    const double* ga = MG[ci] + (long long)r * (a + nu * (kk + o1));
-                    const double* gb = MG[ci] + (long long)r * (bb + nu * (kk + o2));
-                    double s = 0.0;
-                    for (int l = 0; l < r; ++l) s = add_(s, mul_(mul_(ga[l], Wt[ci][l]), gb[l]));
-                    run[ci] = add_(run[ci], s);
-                }
+                for (int kk = done[ci]; kk <= kk_hi; ++kk) run[ci] = add_(run[ci], wdot(base_a + rnu * kk, Wt[ci], base_b + rnu * kk, r));
                 done[ci] = kk_hi + 1;
                 contrib = run[ci];
             } else {
-                const int kk_lo = max(F.i0 - jmax, 0);
                 contrib = 0.0;
-                for (int kk = kk_lo; kk <= kk_hi; ++kk) {
-                    const double* ga = MG[ci] + (long long)r * (a + nu * (kk + jmax - j1));
-                    const double* gb = MG[ci] + (long long)r * (bb + nu * (kk + jmax - j2));
-                    double s = 0.0;
-                    for (int l = 0; l < r; ++l) s = add_(s, mul_(mul_(ga[l], Wt[ci][l]), gb[l]));
-                    contrib = add_(contrib, s);
-                }
+                for (int kk = max(F.i0 - jmax, 0); kk <= kk_hi; ++kk)
+                    contrib = add_(contrib, wdot(base_a + rnu * kk, Wt[ci], base_b + rnu * kk, r));
             }
             val = add_(val, contrib);
         }
-        Q[(off + j1 * nu + a) + (long long)(off + j2 * nu + bb) * nvar] = val;
+        *qout = val;
     }
 }
 
-__global__ void k2_assemble_q_kernel(const __grid_constant__ BuildParams P)
+// `staged`: the per-instance M A^k B tables and weights of every step-size cost are first copied to shared memory, so the
+// sequential walk down each block diagonal runs at shared-memory instead of L2 latency (host checks that they fit).
+__global__ void k2_assemble_q_kernel(const __grid_constant__ BuildParams P, int staged)
 {
+    extern __shared__ double stage_sm[];
     const int nchain = (2 * P.N - 1) * P.nu * P.nu;
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch < nchain) dev_q_chain(P, blockIdx.y, ch);
+    const int b = blockIdx.y;
+    const double* MG[kMaxCost];
+    const double* Wt[kMaxCost];
+    int o = 0;
+    for (int ci = 0; ci < P.ncost; ++ci) {
+        const CostFam& F = P.cost[ci];
+        MG[ci] = F.MGx + (long long)b * F.sMGx;
+        Wt[ci] = F.w.at(b);
+        if (!staged || F.dense) continue;
+        for (int t = threadIdx.x; t < int(F.sMGx); t += blockDim.x) stage_sm[o + t] = MG[ci][t];
+        MG[ci] = stage_sm + o;
+        o += int(F.sMGx);
+        for (int t = threadIdx.x; t < F.rows; t += blockDim.x) stage_sm[o + t] = Wt[ci][t];
+        Wt[ci] = stage_sm + o;
+        o += F.rows;
+    }
+    if (staged) __syncthreads();
+    if (ch < nchain) dev_q_chain(P, b, ch, MG, Wt, nullptr);
+}
+
+// Small Hessians (nU^2 doubles fit shared memory next to the staged cost tables): one CTA per instance assembles Q in a
+// shared-memory tile.  Work is balanced by giving every thread the block diagonal dd = p (N - p steps) AND its
+// complement dd = p - N (p steps): N steps per thread.  Costs are the outer loop, so their descriptors live in
+// registers; every entry still receives  ((qdiag + cost_0) + cost_1) + ...  with each cost's running sum over kk
+// ascending -- the reference accumulation order.  The tile is written out coalesced.
+__global__ void k2_assemble_q_tiled_kernel(const __grid_constant__ BuildParams P)
+{
+    const int nu = P.nu, N = P.N, nU = P.nU, nvar = P.nvar;
+    const int b = blockIdx.x;
+    int mgo[kMaxCost], wto[kMaxCost];
+    int o = 0;
+    for (int ci = 0; ci < P.ncost; ++ci) {
+        const CostFam& F = P.cost[ci];
+        mgo[ci] = wto[ci] = 0;
+        if (F.dense) continue;
+        stage_copy(o, F.MGx + (long long)b * F.sMGx, int(F.sMGx));
+        mgo[ci] = o;
+        o += int(F.sMGx);
+        stage_copy(o, F.w.at(b), F.rows);
+        wto[ci] = o;
+        o += F.rows;
+    }
+    const int tile = o;
+    for (int idx = threadIdx.x; idx < nU * nU; idx += blockDim.x) stage_sm[tile + idx] = (idx % nU == idx / nU) ? P.qdiag : 0.0;
+    __syncthreads();
+    const int qstep = nu * (nU + 1);
+    for (int t = threadIdx.x; t < N * nu * nu; t += blockDim.x) {
+        const int a = t % nu, bb = (t / nu) % nu, pidx = t / (nu * nu);
+        // virtual chain of exactly N steps: block diagonal dd = pidx for the first N - pidx steps (jmax = N-1 .. pidx),
+        // then dd = pidx - N for the remaining pidx steps (jmax = N-1 .. N-pidx): every lane of a warp runs N steps
+        const int len0 = N - pidx;
+        for (int ci = 0; ci < P.ncost; ++ci) {
+            const CostFam& F = P.cost[ci];
+            if (F.dense) continue; // added afterwards by the GEMM path (Q += T'WT)
+            const int r = F.rows, rnu = r * nu, i0 = F.i0, i1 = F.i1, wo = wto[ci];
+            int ga = mgo[ci] + r * a, gb = mgo[ci] + r * (bb + nu * pidx);               // dd = pidx: o1 = 0, o2 = dd
+            int qp = tile + ((N - 1) * nu + a) + ((N - 1 - pidx) * nu + bb) * nU;         // its entry at jmax = N-1
+            double run = 0.0;
+            int kk = 0, jmax = N - 1;
+            for (int sidx = 0; sidx < N; ++sidx, --jmax, qp -= qstep) {
+                if (sidx == len0) { // switch to dd = pidx - N: o1 = N - pidx, o2 = 0
+                    ga = mgo[ci] + r * (a + nu * (N - pidx));
+                    gb = mgo[ci] + r * bb;
+                    qp = tile + ((pidx - 1) * nu + a) + ((N - 1) * nu + bb) * nU;
+                    run = 0.0;
+                    kk = 0;
+                    jmax = N - 1;
+                }
+                const int kk_hi = i1 - 1 - jmax;
+                if (kk_hi < 0) continue;
+                double contrib;
+                if (i0 == 0) {
+                    for (; kk <= kk_hi; ++kk) {
+                        const int oa = ga + rnu * kk, ob = gb + rnu * kk;
+                        double sd = 0.0;
+                        for (int l = 0; l < r; ++l) sd = add_(sd, mul_(mul_(stage_sm[oa + l], stage_sm[wo + l]), stage_sm[ob + l]));
+                        run = add_(run, sd);
+                    }
+                    contrib = run;
+                } else {
+                    contrib = 0.0;
+                    for (int k2 = max(i0 - jmax, 0); k2 <= kk_hi; ++k2) {
+                        const int oa = ga + rnu * k2, ob = gb + rnu * k2;
+                        double sd = 0.0;
+                        for (int l = 0; l < r; ++l) sd = add_(sd, mul_(mul_(stage_sm[oa + l], stage_sm[wo + l]), stage_sm[ob + l]));
+                        contrib = add_(contrib, sd);
+                    }
+                }
+                stage_sm[qp] = add_(stage_sm[qp], contrib);
+            }
+        }
+    }
+    __syncthreads();
+    const int off = P.initial_state ? P.nx : 0;
+    double* Q = P.Q + (long long)b * nvar * nvar + off + (long long)off * nvar;
+    if (off == 0 && nvar == nU) {
+        for (int idx = threadIdx.x; idx < nU * nU; idx += blockDim.x) Q[idx] = stage_sm[tile + idx];
+    } else {
+        for (int idx = threadIdx.x; idx < nU * nU; idx += blockDim.x) {
+            const int i = idx % nU, j = idx / nU;
+            Q[i + (long long)j * nvar] = stage_sm[tile + idx];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
 // K2c: per-cost E (nx x nU) and f (nU):  E = sum_i MPhi_i' W T_i, f = sum_i res_i' W T_i
 // (src/costFunctions.cpp:77-78,105-106,210-211).  One thread per (s|f, column).  grid = (tiles, batch)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void dev_ef(const BuildParams& P, int b, int t)
+template <bool STAGED>
+__device__ __forceinline__ void dev_ef(const BuildParams& P, int b, int t, int ci, Tab<STAGED> MG, Tab<STAGED> MPhi, Tab<STAGED> res,
+    Tab<STAGED> w)
 {
     const int nx = P.nx, nu = P.nu, nU = P.nU;
-    const int per = (nx + 1) * nU;
-    const int ci = t / per, rem = t % per;
-    const int s = rem % (nx + 1), col = rem / (nx + 1);
+    const int s = t % (nx + 1), col = t / (nx + 1);
     const int j = col / nu, bb = col % nu;
     const CostFam& F = P.cost[ci];
-    if (F.dense) return;
     const int r = F.rows;
-    const double* MG = F.MGx + (long long)b * F.sMGx;
-    const double* MPhi = F.MPhi + (long long)b * F.sMPhi;
-    const double* res = F.res + (long long)b * F.sres;
-    const double* w = F.w.at(b);
     double acc = 0.0;
-    for (int i = max(F.i0, j); i < F.i1; ++i) {
-        const int ii = i - F.i0;
-        const double* g = MG + (long long)r * (bb + nu * (i - j));
-        const double* lhs = (s < nx) ? MPhi + (long long)r * (s + nx * ii) : res + (long long)r * ii;
-        double sum = 0.0;
-        for (int l = 0; l < r; ++l) sum = add_(sum, mul_(mul_(lhs[l], w[l]), g[l]));
-        acc = add_(acc, sum);
+    {
+        const int ibeg = max(F.i0, j);
+        Tab<STAGED> g = MG.shifted(r * (bb + nu * (ibeg - j)));
+        Tab<STAGED> lhs = (s < nx) ? MPhi.shifted(r * (s + nx * (ibeg - F.i0))) : res.shifted(r * (ibeg - F.i0));
+        const int gstep = r * nu, lstep = (s < nx) ? r * nx : r;
+        int go = 0, lo = 0;
+        for (int i = ibeg; i < F.i1; ++i, go += gstep, lo += lstep) {
+            double sum = 0.0;
+            if (r == 1) sum = add_(sum, mul_(mul_(lhs[lo], w[0]), g[go]));
+            else
+                for (int l = 0; l < r; ++l) sum = add_(sum, mul_(mul_(lhs[lo + l], w[l]), g[go + l]));
+            acc = add_(acc, sum);
+        }
     }
     if (s < nx) F.E[(long long)b * F.sE + s + (long long)col * nx] = acc;
     else F.f[(long long)b * F.sf + col] = acc;
+    (void)nU;
 }
 
-__global__ void k2_assemble_ef_kernel(const __grid_constant__ BuildParams P)
+// grid = (tiles over (nx+1) nU, batch, cost); STAGED: this cost's tables are first copied to shared memory
+template <bool STAGED> __global__ void k2_assemble_ef_kernel(const __grid_constant__ BuildParams P)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < (P.nx + 1) * P.nU * P.ncost) dev_ef(P, blockIdx.y, t);
+    const int b = blockIdx.y, ci = blockIdx.z;
+    const CostFam& F = P.cost[ci];
+    if (F.dense) return;
+    Tab<STAGED> MG{ F.MGx + (long long)b * F.sMGx, 0 };
+    Tab<STAGED> MPhi{ F.MPhi + (long long)b * F.sMPhi, 0 };
+    Tab<STAGED> res{ F.res + (long long)b * F.sres, 0 };
+    Tab<STAGED> w{ F.w.at(b), 0 };
+    if (STAGED) {
+        int o = 0;
+        stage_copy(o, MG.g, int(F.sMGx)); MG.o = o; o += int(F.sMGx);
+        stage_copy(o, MPhi.g, int(F.sMPhi)); MPhi.o = o; o += int(F.sMPhi);
+        stage_copy(o, res.g, int(F.sres)); res.o = o; o += int(F.sres);
+        stage_copy(o, w.g, F.rows); w.o = o;
+        __syncthreads();
+    }
+    if (t < (P.nx + 1) * P.nU) dev_ef<STAGED>(P, b, t, ci, MG, MPhi, res, w);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -633,28 +837,33 @@ __global__ void __launch_bounds__(kSmT, 4) k4_schur_small_kernel(const __grid_co
 //   convolution sum_{j<i} G_{i-1-j} u_j straight from the compact Gs.  One thread per trajectory row.
 // grid = (row tiles over X, batch)
 // ------------------------------------------------------------------------------------------------
-__global__ void k7_results_kernel(const __grid_constant__ BuildParams P, const double* __restrict__ xres,
-    double* __restrict__ control, double* __restrict__ traj)
+template <bool STAGED>
+__global__ void k7_results_kernel(const __grid_constant__ BuildParams P, const double* __restrict__ xres, double* __restrict__ control,
+    double* __restrict__ traj)
 {
     const int nx = P.nx, nu = P.nu, N = P.N, X = P.X, nU = P.nU, nvar = P.nvar;
     const int off = P.initial_state ? nx : 0;
-    const long long NX = (long long)N * nx;
+    const int NX = N * nx;
     const int b = blockIdx.y;
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    const double* xr = xres + (long long)b * nvar;
+    // the solution and the compact Psi column block are read N times per row: keep them in shared memory when they fit
+    Tab<STAGED> xr{ xres + (long long)b * nvar, 0 };
+    Tab<STAGED> Gs{ P.Gs + (long long)b * NX * nu, nvar };
+    if (STAGED) {
+        stage_copy(0, xr.g, nvar);
+        stage_copy(nvar, Gs.g, NX * nu);
+        __syncthreads();
+    }
     if (control && row < nU) control[(long long)b * nU + row] = xr[off + row];
     if (!traj || row >= X) return;
-    const double* x0 = P.initial_state ? xr : P.x0.at(b);
     const double* Phi = P.Phi + (long long)b * X * nx;
-    const double* Gs = P.Gs + (long long)b * NX * nu;
     const int i = row / nx, r = row % nx;
     double s1 = 0.0;
-    for (int a = 0; a < nx; ++a) s1 = add_(s1, mul_(Phi[row + (long long)a * X], x0[a]));
+    for (int a = 0; a < nx; ++a) s1 = add_(s1, mul_(Phi[row + (long long)a * X], P.initial_state ? xr[a] : P.x0.at(b)[a]));
     double s2 = 0.0;
-    for (int j = 0; j < i; ++j) {
-        const double* g = Gs + (long long)(i - 1 - j) * nx + r;
-        for (int cc = 0; cc < nu; ++cc) s2 = add_(s2, mul_(g[(long long)cc * NX], xr[off + j * nu + cc]));
-    }
+    int go = (i - 1) * nx + r; // G_{i-1-j}[r, :]
+    for (int j = 0; j < i; ++j, go -= nx)
+        for (int cc = 0; cc < nu; ++cc) s2 = add_(s2, mul_(Gs[go + cc * NX], xr[off + j * nu + cc]));
     traj[(long long)b * X + row] = add_(add_(s1, s2), P.xi[(long long)b * X + row]);
 }
 
@@ -694,7 +903,17 @@ int k2k4_assemble_launch(const BuildParams& P, double* schur_ws, long long schur
     }
     {
         const int nchain = (2 * P.N - 1) * P.nu * P.nu;
-        k2_assemble_q_kernel<<<dim3(ceil_div(nchain, 128), nb), 128, 0, st>>>(P);
+        size_t need = 0; // staged tables: M A^k B blocks + weights of every step-size cost
+        for (int i = 0; i < P.ncost; ++i) if (!P.cost[i].dense) need += size_t(P.cost[i].sMGx) + P.cost[i].rows;
+        const int staged = need * sizeof(double) <= 40 * 1024;
+        // small Hessians: one CTA per instance assembles Q in a shared-memory tile and writes it out coalesced
+        const size_t tile = size_t(nU) * nU;
+        const int tiled = staged && (need + tile) * sizeof(double) <= 44 * 1024;
+        if (tiled) {
+            const int threads = std::min(256, std::max(32, ceil_div(P.N * P.nu * P.nu, 32) * 32));
+            k2_assemble_q_tiled_kernel<<<nb, threads, (need + tile) * sizeof(double), st>>>(P);
+        } else
+            k2_assemble_q_kernel<<<dim3(ceil_div(nchain, 128), nb), 128, staged ? need * sizeof(double) : 0, st>>>(P, staged);
         CB_CHECK_LAUNCH();
     }
     const long long sPsi = (long long)X * nU, sPhi = (long long)X * nx;
@@ -714,8 +933,13 @@ int k2k4_assemble_launch(const BuildParams& P, double* schur_ws, long long schur
         CB_GEMM(1, 1, nU, R, 1.0, F.res, R, F.sres, F.WT, R, F.sT, 0.0, F.f, 1, F.sf, nb, st);
     }
     if (P.ncost > 0) {
-        const int nef = (nx + 1) * nU * P.ncost;
-        k2_assemble_ef_kernel<<<dim3(ceil_div(nef, 128), nb), 128, 0, st>>>(P);
+        size_t need = 0; // largest single cost: its M A^k B, M Phi_i, residual tables and weights
+        for (int i = 0; i < P.ncost; ++i)
+            if (!P.cost[i].dense)
+                need = std::max(need, size_t(P.cost[i].sMGx) + size_t(P.cost[i].sMPhi) + size_t(P.cost[i].sres) + P.cost[i].rows);
+        const dim3 grid(ceil_div((nx + 1) * nU, 128), nb, P.ncost);
+        if (need * sizeof(double) <= 40 * 1024) k2_assemble_ef_kernel<true><<<grid, 128, need * sizeof(double), st>>>(P);
+        else k2_assemble_ef_kernel<false><<<grid, 128, 0, st>>>(P);
         CB_CHECK_LAUNCH();
     }
     for (int fi = 0; fi < P.nfam; ++fi) { // full-size constraints: rows = E Psi (+G), Y = E Phi, z = f - E xi
@@ -782,7 +1006,11 @@ int k7_results_launch(const BuildParams& P, const double* x, double* control, do
 {
     if (P.batch > 65535) return -int(cudaErrorInvalidValue);
     const int rows = std::max(P.X, P.nU);
-    k7_results_kernel<<<dim3(ceil_div(rows, 128), P.batch), 128, 0, st>>>(P, x, control, trajectory);
+    const size_t need = sizeof(double) * (size_t(P.nvar) + size_t(P.N) * P.nx * P.nu);
+    const int staged = need <= 40 * 1024;
+    const dim3 grid(ceil_div(rows, 128), P.batch);
+    if (staged) k7_results_kernel<true><<<grid, 128, need, st>>>(P, x, control, trajectory);
+    else k7_results_kernel<false><<<grid, 128, 0, st>>>(P, x, control, trajectory);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 1 : -int(e);
 }
