@@ -11,7 +11,7 @@ namespace cb {
 namespace {
 
 constexpr int kChains = 8;
-constexpr int kInner = 4096;
+constexpr int kInner = 1024;
 
 __global__ void __launch_bounds__(256) dfma_chain_kernel(double* out, double a, double b)
 {

@@ -190,10 +190,11 @@ __device__ inline bool gs_factor(double* __restrict__ J, int ld, int n, int n2, 
 {
     const int tid = threadIdx.x, lane = lane_id(), g = tid >> 5;
     double akk = J[0];
+    if (!(akk > 0.0)) return false;
+    double rkk = sqrt(akk), inv = 1.0 / rkk;
     for (int k = 0; k < n; ++k) {
-        if (!(akk > 0.0)) return false;
-        const double rkk = sqrt(akk);
-        const double inv = 1.0 / rkk;
+        // the next pivot before this step's sweep touches it (nobody writes J until the barrier)
+        const double anext = (k + 1 < n) ? J[(k + 1) + size_t(k + 1) * ld] : 1.0;
         if (tid < n2) {
             double c;
             if (tid < k) c = J[tid + size_t(k) * ld] * (-inv);
@@ -206,6 +207,16 @@ __device__ inline bool gs_factor(double* __restrict__ J, int ld, int n, int n2, 
             coef[tid] = c;
         }
         __syncthreads();
+        // pivot k+1 after this step's update, computed by every thread exactly as the sweep computes it; its square
+        // root and reciprocal (two long dependent chains) are issued here and overlap with the sweep below
+        double rnext = 1.0, inext = 1.0;
+        bool pd = true;
+        if (k + 1 < n) {
+            const double a2 = fma(mult[k + 1], coef[k + 1], anext);
+            pd = a2 > 0.0;
+            rnext = sqrt(a2);
+            inext = 1.0 / rnext;
+        }
         if (tid <= k) J[tid + size_t(k) * ld] = coef[tid]; // column k of the inverse (dpori), diagonal = 1/R[k,k]
         {
             const int i0 = 2 * lane, i1 = i0 + 1;
@@ -214,14 +225,16 @@ __device__ inline bool gs_factor(double* __restrict__ J, int ld, int n, int n2, 
                 for (int j = max(k + 1, i0) + ((g - max(k + 1, i0)) & 3); j < n; j += 4) {
                     double2 a = ld2(J + i0 + size_t(j) * ld);
                     const double mj = mult[j];
-                    a.x = ((i0 == k) ? 0.0 : a.x) + mj * c.x;
-                    if (i1 <= j) a.y = ((i1 == k) ? 0.0 : a.y) + mj * c.y;
+                    a.x = fma(mj, c.x, (i0 == k) ? 0.0 : a.x);
+                    if (i1 <= j) a.y = fma(mj, c.y, (i1 == k) ? 0.0 : a.y);
                     *reinterpret_cast<double2*>(J + i0 + size_t(j) * ld) = a;
                 }
             }
         }
         __syncthreads();
-        if (k + 1 < n) akk = J[(k + 1) + size_t(k + 1) * ld];
+        if (!pd) return false;
+        rkk = rnext;
+        inv = inext;
     }
     // strict lower triangle := 0 (qpgen2 label 21); pad row/column are zeroed by the caller
     for (int idx = tid; idx < n2 * n2; idx += kSmT) {
@@ -402,18 +415,21 @@ __device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, do
                     }
                 }
                 MinIdx tc; tc.v = 0.0; tc.i = -1;
-                if (tid < nact) {
-                    const double* srow = S + W.rowmap[tid];
-                    double s0 = 0.0, s1 = 0.0;
-                    int k = 0;
-                    for (; k + 1 < nact; k += 2) {
-                        s0 += srow[size_t(k) * lds] * W.d[k];
-                        s1 += srow[size_t(k + 1) * lds] * W.d[k + 1];
+                {
+                    // r = S d1: two lanes per active row (even / odd k), i.e. all four warps share the sweep -- with S in
+                    // L2 (SG) this is the longest chain of the phase.  s0 (even k) + s1 (odd k) as before.
+                    const int row = tid >> 1, half = tid & 1;
+                    double sh = 0.0;
+                    if (row < nact) {
+                        const double* srow = S + W.rowmap[row];
+                        for (int k = half; k < nact; k += 2) sh += srow[size_t(k) * lds] * W.d[k];
                     }
-                    if (k < nact) s0 += srow[size_t(k) * lds] * W.d[k];
-                    s0 += s1;
-                    W.r[tid] = s0;
-                    if (W.iact[tid] - 1 >= meq && s0 > 0.0) { tc.v = W.u[tid] / s0; tc.i = tid; }
+                    const double other = __shfl_xor_sync(0xffffffffu, sh, 1);
+                    if (half == 0 && row < nact) {
+                        const double s0 = sh + other;
+                        W.r[row] = s0;
+                        if (W.iact[row] - 1 >= meq && s0 > 0.0) { tc.v = W.u[row] / s0; tc.i = row; }
+                    }
                 }
                 double dd = 0.0;
                 if (tid >= nact && tid < n) { const double dj = W.d[tid]; dd = dj * dj; }
