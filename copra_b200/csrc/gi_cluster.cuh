@@ -473,7 +473,7 @@ __device__ inline int gc_solve(const GiView& P, const GcLayout& L, GcWork& W, do
                 // ---- DROP the it1-th active constraint -------------------------------------------------------
                 __syncthreads();
                 const int p = it1;
-                const int dropped = W.iact[p] - 1;
+                const int dropped = (tid == 0) ? W.iact[p] - 1 : 0; // used by thread 0 only, which also clears iact below
                 const int prow = W.rowmap[p];
                 if (nact > 1) {
                     // w = (row p of S) - gamma e_last ; t = tau w   (every CTA redundantly; row p is not modified below)
@@ -516,7 +516,7 @@ __device__ inline int gc_solve(const GiView& P, const GcLayout& L, GcWork& W, do
                     __syncthreads();
                 }
                 if (tid == 0) {
-                    W.u[nact - 1] = W.u[nact];
+                        W.u[nact - 1] = W.u[nact];
                     W.u[nact] = 0.0;
                     W.iact[nact - 1] = 0;
                     W.active[dropped] = 0;

@@ -517,7 +517,7 @@ __device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, do
                     // ---- DROP the it1-th active constraint --------------------------------------------------
                     __syncthreads(); // u updates visible; redv free
                     const int p = it1;
-                    const int dropped = W.iact[p] - 1;
+                    const int dropped = (tid == 0) ? W.iact[p] - 1 : 0; // used by thread 0 only, which also clears iact below
                     const int prow = W.rowmap[p];
                     if (nact > 1) {
                         // v = row p of S ; rho = |v| ; w = v - gamma e_last ; tw = tau w

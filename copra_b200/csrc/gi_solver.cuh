@@ -500,7 +500,7 @@ __device__ inline int gi_solve(const GiView& P, GiWork& W, const GiOut& O, doubl
                     // ---- drop the it1-th active constraint: reflection with last column ~ row p of S ----
                     __syncthreads(); // u updates visible
                     const int p = it1;
-                    const int dropped = W.iact[p] - 1;
+                    const int dropped = (tid == 0) ? W.iact[p] - 1 : 0; // used by thread 0 only, which also clears iact below
                     const int prow = W.rowmap[p];
                     if (nact > 1) {
                         // v = row p of S (nact entries); rho = |v|; w = v - gamma e_last; d := tau * w
