@@ -14,6 +14,9 @@
 // one CTA per instance, and handed over through global memory.
 // Three cluster barriers per active-set iteration.  Same iterates as gi_solver.cuh / qpgen2.
 #pragma once
+#ifdef GC_PROFILE
+#include <cstdio>
+#endif
 #include "common.cuh"
 #include "engine.cuh"
 #include "gi_solver.cuh"
@@ -28,7 +31,9 @@ constexpr int kClMaxC = 8;
 
 struct GcLayout {
     int n, C, nr, ld, seg, mshare, threads;
-    size_t oJ, oX, oD, oZ, oV, oR, oU, oA, oW, oT, oLb, oUb, oRecv, oNorm, oPart, oRed, oCand, oRowbuf; // doubles
+    int nb;          // pivots per block step of the distributed factorisation (panel rows that fit the scratch region)
+    size_t scratch;  // doubles from oX that are free while the factorisation runs (x d z v r a w t recv part)
+    size_t oJ, oX, oD, oZ, oV, oR, oU, oA, oW, oT, oLb, oUb, oRecv, oNorm, oPart, oRed, oCand; // doubles
     size_t oIact, oRowmap, oRedI, oCtl, oActive, oSgn, bytes;                        // bytes
 };
 
@@ -43,13 +48,21 @@ __host__ __device__ inline GcLayout gc_layout(int n, int meq, int m, int C, int 
     size_t o = 0;
     auto take = [&](size_t cnt) { size_t at = o; o += (cnt + 1) & ~size_t(1); return at; };
     L.oJ = take(size_t(L.ld) * n);
-    L.oX = take(n); L.oD = take(n); L.oZ = take(size_t(L.nr) * C); L.oV = take(n); L.oR = take(n); L.oU = take(n + 2);
-    L.oA = take(L.nr); L.oW = take(L.nr); L.oT = take(n); L.oLb = take(n); L.oUb = take(n);
+    // iteration vectors that hold nothing while the factorisation runs come first and contiguously: the factorisation
+    // aliases them as its broadcast panel (nb pivot rows) and per-row coefficient table
+    L.oX = take(n); L.oD = take(n); L.oZ = take(size_t(L.nr) * C); L.oV = take(n); L.oR = take(n);
+    L.oA = take(L.nr); L.oW = take(L.nr); L.oT = take(n);
     L.oRecv = take(size_t(L.seg) * C);
-    L.oNorm = take(L.mshare);
     L.oPart = take(2 * size_t(threads) + 64);
+    L.scratch = o - L.oX;
+    {
+        const size_t per = size_t(n) + 2 + size_t(L.nr) + 2; // panel row + coefficient column + reciprocal, per pivot
+        const size_t fit = L.scratch / per;
+        L.nb = int(fit < 1 ? 1 : (fit > 8 ? 8 : fit));
+    }
+    L.oU = take(n + 2); L.oLb = take(n); L.oUb = take(n);
+    L.oNorm = take(L.mshare);
     L.oRed = take(4 * kMaxWarps);
-    L.oRowbuf = take(2 * (size_t(n) + 2)); // broadcast pivot rows of the distributed factorisation (double buffered)
     L.oCand = take(8 * kClMaxC); // per-rank slots: [3r..3r+2] arg-min candidate, [3C+2r..] partial scalars
     size_t b = o * sizeof(double);
     L.oIact = b; b += sizeof(int) * size_t(n);
@@ -63,7 +76,7 @@ __host__ __device__ inline GcLayout gc_layout(int n, int meq, int m, int C, int 
 }
 
 struct GcWork {
-    double *J, *x, *d, *z, *v, *r, *u, *a, *w, *t, *lb, *ub, *recv, *norm, *part, *red, *cand, *rowbuf;
+    double *J, *x, *d, *z, *v, *r, *u, *a, *w, *t, *lb, *ub, *recv, *norm, *part, *red, *cand;
     int *iact, *rowmap, *redi, *ctl;
     unsigned char* active;
     signed char* sgn;
@@ -75,7 +88,7 @@ __device__ inline GcWork gc_carve(const GcLayout& L, unsigned char* smem)
     double* b = reinterpret_cast<double*>(smem);
     W.J = b + L.oJ; W.x = b + L.oX; W.d = b + L.oD; W.z = b + L.oZ; W.v = b + L.oV; W.r = b + L.oR; W.u = b + L.oU;
     W.a = b + L.oA; W.w = b + L.oW; W.t = b + L.oT; W.lb = b + L.oLb; W.ub = b + L.oUb; W.recv = b + L.oRecv; W.norm = b + L.oNorm; W.part = b + L.oPart;
-    W.red = b + L.oRed; W.cand = b + L.oCand; W.rowbuf = b + L.oRowbuf;
+    W.red = b + L.oRed; W.cand = b + L.oCand;
     W.iact = reinterpret_cast<int*>(smem + L.oIact);
     W.rowmap = reinterpret_cast<int*>(smem + L.oRowmap);
     W.redi = reinterpret_cast<int*>(smem + L.oRedI);
@@ -101,6 +114,9 @@ __device__ inline int gc_solve(const GiView& P, const GcLayout& L, GcWork& W, do
     double* __restrict__ J = W.J;
     double* scal = W.red + 2 * kMaxWarps;
 
+#ifdef GC_PROFILE
+    long long tp0 = clock64(), tp1 = 0, tp2 = 0, tp3 = 0, ta = 0, tb = 0, tg = 0, td = 0, tmark = 0;
+#endif
     // ---- load my slab of Q --------------------------------------------------------------------------
     for (int idx = tid; idx < nrc * n; idx += T) {
         const int r = idx % nrc, c = idx / nrc;
@@ -125,37 +141,163 @@ __device__ inline int gc_solve(const GiView& P, const GcLayout& L, GcWork& W, do
     }
     __syncthreads();
 
-    // ---- distributed Cholesky Q = R'R (upper; dpofa's result, right-looking): the owner of row k scales
-    // it and writes it into every CTA's row buffer through DSMEM; one cluster barrier per k -------------
+#ifdef GC_PROFILE
+    tp1 = clock64();
+#endif
+    // ---- distributed, blocked factorisation: Q = R'R (LINPACK dpofa) and J = R^-1 (dpori) in ONE pass ----------
+    // Per pivot p the fused sweep is  J[i,j] = (i == p ? 0 : J[i,j]) + mult_p[j] * coef_p[i]  (j > p, i <= j) with
+    // mult_p = row p of R and coef_p[i] = -J[i,p]/R[p,p] (i < p), 1/R[p,p] (i == p), -R[p,i] (i > p): every entry sees
+    // the same updates in the same order as the two LINPACK loops.  Pivots are taken nb at a time (a block never
+    // straddles two slabs): the owner factors its nb rows locally (block barriers only), broadcasts them as one panel
+    // (the peers pull it through DSMEM), and every CTA applies a rank-nb update to its slab -- two cluster barriers
+    // per nb pivots instead of two per pivot.
     bool pd = true;
-    for (int k = 0; k < n; ++k) {
-        const int owner = k / L.nr, kk = k - owner * L.nr;
-        double* rb = W.rowbuf + (k & 1) * (n + 2);
-        if (rank == owner) {
-            const double akk = J[kk + size_t(k) * ld];
-            const bool ok = akk > 0.0;
-            const double rkk = ok ? sqrt(akk) : 1.0;
-            for (int j = k + tid; j < n; j += T) {
-                const double v = (j == k) ? rkk : J[kk + size_t(j) * ld] / rkk;
-                J[kk + size_t(j) * ld] = v;
-                for (int t = 0; t < C; ++t) cluster.map_shared_rank(rb, t)[j] = v;
+    {
+        const int NB = L.nb, pstride = n + 2;
+        double* panel = W.x;                                   // NB x (n+2): [pp][j] = R[p,j] (j >= p), [pp][n] = pivot ok
+        double* coefb = panel + size_t(NB) * pstride;          // nr x NB   : coef_p[i] for my rows
+        double* invb = coefb + size_t(L.nr) * NB;              // NB        : 1 / R[p,p]
+#ifdef GC_PROFILE
+        long long f1 = 0, f2 = 0, f3 = 0, f4 = 0, f5 = 0, fm = clock64();
+#define GC_TICK(acc) { const long long t_ = clock64(); acc += t_ - fm; fm = t_; }
+#else
+#define GC_TICK(acc)
+#endif
+        for (int k0 = 0; k0 < n;) {
+            const int owner = k0 / L.nr;
+            const int k1 = min(min(k0 + NB, n), (owner + 1) * L.nr), nb = k1 - k0;
+            if (rank == owner) {
+                bool ok = true;
+                for (int p = k0; p < k1; ++p) {
+                    const int pp = p - k0, lr = p - r0;
+                    double* prow = panel + size_t(pp) * pstride;
+                    const double akk = J[lr + size_t(p) * ld];
+                    ok = ok && akk > 0.0;
+                    const double rkk = ok ? sqrt(akk) : 1.0;
+                    for (int j = p + tid; j < n; j += T) {
+                        const double v = (j == p) ? rkk : J[lr + size_t(j) * ld] / rkk;
+                        J[lr + size_t(j) * ld] = v;
+                        prow[j] = v;
+                    }
+                    if (tid == 0) prow[n] = ok ? 1.0 : 0.0;
+                    __syncthreads();
+                    // the rest of my block rows: A[i,j] -= R[p,i] R[p,j], p < i < k1, j >= i.  One thread per column (the slab's
+                    // leading dimension is odd, so a warp walking along a row is conflict-free), rows in a short loop.
+                    const int rows = k1 - 1 - p;
+                    if (rows > 0) {
+                        for (int c_ = p + 1 + tid; c_ < n; c_ += T) {
+                            const double mc = prow[c_];
+                            double* col = J + lr + 1 + size_t(c_) * ld;
+                            const int rmax = min(rows, c_ - p); // rows i = p+1+r_ with i <= c_
+                            for (int r_ = 0; r_ < rmax; ++r_) col[r_] = fma(mc, -prow[p + 1 + r_], col[r_]);
+                        }
+                        __syncthreads();
+                    }
+                }
             }
-            if (tid == 0) for (int t = 0; t < C; ++t) cluster.map_shared_rank(rb, t)[n] = ok ? 1.0 : 0.0;
-        }
-        cluster.sync();
-        if (rb[n] == 0.0) { pd = false; break; }
-        // A[i,j] -= R[k,i] R[k,j] for my rows i > k, j >= i
-        {
-            const int rlo = max(0, k + 1 - r0); // my rows with global index > k
-            if (rlo < nrc) {
-                double* Jl = J + rlo;
-                const int ib = r0 + rlo;
-                tile_rc(nrc - rlo, ib, n, [&](int r_, int c_) {
-                    if (c_ >= ib + r_) Jl[r_ + size_t(c_) * ld] -= rb[ib + r_] * rb[c_];
-                });
+            GC_TICK(f1)
+            cluster.sync();
+            GC_TICK(f2)
+            if (rank != owner) {
+                // PULL the panel (columns >= k0 and the flags) from the owner's shared memory: the copy is issued by all the
+                // peers' SMs in parallel (an owner-side push of nb x n x (C-1) remote stores was issue-bound on one SM)
+                const double* src = cluster.map_shared_rank(panel, owner);
+                const int width = pstride - k0;
+                for (int idx = tid; idx < nb * width; idx += T) {
+                    const int pp = idx / width, j = k0 + (idx - pp * width);
+                    panel[size_t(pp) * pstride + j] = src[size_t(pp) * pstride + j];
+                }
+                __syncthreads();
             }
+            for (int pp = 0; pp < nb; ++pp) pd = pd && panel[size_t(pp) * pstride + n] != 0.0;
+            if (!pd) break;
+            GC_TICK(f3)
+            if (tid < nb) invb[tid] = 1.0 / panel[size_t(tid) * pstride + k0 + tid];
+            __syncthreads();
+            // coefficients of my rows, pivot by pivot (a short serial fold per row), and the finished columns k0..k1-1
+            for (int r = tid; r < nrc; r += T) {
+                const int i = r0 + r;
+                for (int pp = 0; pp < nb; ++pp) {
+                    const int p = k0 + pp;
+                    double c;
+                    if (i > p) c = -panel[size_t(pp) * pstride + i];
+                    else if (i == p) c = invb[pp];
+                    else {
+                        // J[i,p] as the sweeps of the earlier pivots of this block leave it (those with q < i were already
+                        // applied by the owner's local update when i is one of the block rows)
+                        double a = J[r + size_t(p) * ld];
+                        for (int qq = max(0, i - k0); qq < pp; ++qq)
+                            a = fma(panel[size_t(qq) * pstride + p], coefb[r + size_t(qq) * L.nr], (i == k0 + qq) ? 0.0 : a);
+                        c = a * (-invb[pp]);
+                    }
+                    coefb[r + size_t(pp) * L.nr] = c;
+                    if (i <= p) J[r + size_t(p) * ld] = c;
+                }
+            }
+            __syncthreads();
+            GC_TICK(f4)
+            // rank-nb update of the columns to the right of the block.  With full 8-pivot panels it is a (rows x 8) x (8 x cols)
+            // product on the FP64 tensor cores (DMMA.8x8x4, two k-steps per 8x8 tile of my slab; tiles dealt out to the
+            // warps); entries below the diagonal are updated too -- they are never read and are zeroed at the end.  The
+            // owner's 8 block rows follow the per-pivot rule (pivot p zeroes row p, earlier pivots are already applied),
+            // so they take the scalar path, one thread per column.
+            if (NB == 8) {
+                const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+                const int MT = (nrc + 7) >> 3, NT = (n - k1 + 7) >> 3;
+                const int skip = (rank == owner) ? (k0 - r0) >> 3 : -1; // blocks are 8-aligned inside a slab
+                for (int t = warp; t < MT * NT; t += nwarp) {
+                    const int mt = t % MT, nt = t / MT;
+                    if (mt == skip) continue;
+                    const int ar = (mt << 3) + (lane >> 2), ak = lane & 3;
+                    const double a0 = (ar < nrc && ak < nb) ? coefb[ar + size_t(ak) * L.nr] : 0.0;
+                    const double a1 = (ar < nrc && ak + 4 < nb) ? coefb[ar + size_t(ak + 4) * L.nr] : 0.0;
+                    const int cb_ = k1 + (nt << 3), bc = min(cb_ + (lane >> 2), n - 1);
+                    const double b0 = panel[size_t(ak) * pstride + bc], b1 = panel[size_t(ak + 4) * pstride + bc];
+                    const int cc = cb_ + 2 * (lane & 3);
+                    const bool v0 = ar < nrc && cc < n, v1 = ar < nrc && cc + 1 < n;
+                    double c0_ = v0 ? J[ar + size_t(cc) * ld] : 0.0, c1_ = v1 ? J[ar + size_t(cc + 1) * ld] : 0.0;
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0_), "+d"(c1_) : "d"(a0), "d"(b0));
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0_), "+d"(c1_) : "d"(a1), "d"(b1));
+                    if (v0) J[ar + size_t(cc) * ld] = c0_;
+                    if (v1) J[ar + size_t(cc + 1) * ld] = c1_;
+                }
+                if (rank == owner) {
+                    for (int c_ = k1 + tid; c_ < n; c_ += T) {
+                        for (int rr = 0; rr < nb; ++rr) {
+                            const int r_ = k0 - r0 + rr;
+                            double a = 0.0; // pivot k0+rr zeroes its own row first
+                            for (int pp = rr; pp < nb; ++pp) a = fma(panel[size_t(pp) * pstride + c_], coefb[r_ + size_t(pp) * L.nr], a);
+                            J[r_ + size_t(c_) * ld] = a;
+                        }
+                    }
+                }
+            } else {
+                // scalar fallback (panel narrower than 8 pivots): lanes along my rows, the column range dealt out to thread
+                // groups; a thread's nb coefficients stay in registers for its whole column walk
+                const int rp = max(32, round32(nrc));
+                const int G = max(1, T / rp), g = tid / rp, r_ = tid - g * rp;
+                if (g < G && r_ < nrc) {
+                    const int i = r0 + r_;
+                    const int pp0 = (i >= k0 && i < k1) ? i - k0 : 0; // block rows: pivots before i were applied by the owner
+                    double cf[8];
+#pragma unroll
+                    for (int pp = 0; pp < 8; ++pp) cf[pp] = (pp < nb) ? coefb[r_ + size_t(pp) * L.nr] : 0.0;
+                    for (int c_ = max(k1, i) + ((g - max(k1, i)) % G + G) % G; c_ < n; c_ += G) {
+                        double a = J[r_ + size_t(c_) * ld];
+#pragma unroll
+                        for (int pp = 0; pp < 8; ++pp)
+                            if (pp >= pp0 && pp < nb) a = fma(panel[size_t(pp) * pstride + c_], cf[pp], (i == k0 + pp) ? 0.0 : a);
+                        J[r_ + size_t(c_) * ld] = a;
+                    }
+                }
+            }
+            cluster.sync(); // everyone is done with this panel before the next owner overwrites it
+            GC_TICK(f5)
+            k0 = k1;
         }
-        __syncthreads();
+#ifdef GC_PROFILE
+        if (rank == 0 && tid == 0) printf("GCFACT own=%lld sync1=%lld pull=%lld coef=%lld upd+sync2=%lld\n", f1, f2, f3, f4, f5);
+#endif
     }
     if (!pd) {
         if (rank == 0) {
@@ -168,43 +310,14 @@ __device__ inline int gc_solve(const GiView& P, const GcLayout& L, GcWork& W, do
         }
         return 2;
     }
-    // ---- distributed inverse J = R^-1 (dpori's update order) ---------------------------------------------
-    for (int k = 0; k < n; ++k) {
-        const int owner = k / L.nr, kk = k - owner * L.nr;
-        double* rb = W.rowbuf + (k & 1) * (n + 2);
-        if (rank == owner) {
-            for (int j = k + tid; j < n; j += T) {
-                const double v = J[kk + size_t(j) * ld];
-                for (int t = 0; t < C; ++t) cluster.map_shared_rank(rb, t)[j] = v;
-            }
-        }
-        cluster.sync();
-        const double inv = 1.0 / rb[k];
-        // column k: my rows i < k are scaled by -inv, row k becomes inv
-        for (int r = tid; r < nrc; r += T) {
-            const int i = r0 + r;
-            if (i < k) J[r + size_t(k) * ld] *= -inv;
-            else if (i == k) J[r + size_t(k) * ld] = inv;
-        }
-        __syncthreads();
-        // columns j > k: rows i < k gain t_j * J[i,k]; row k becomes t_j * inv   (t_j = old R[k,j])
-        {
-            const int rhi = min(nrc, k + 1 - r0); // my rows with global index <= k
-            if (rhi > 0) {
-                tile_rc(rhi, k + 1, n, [&](int r_, int c_) {
-                    const int i = r0 + r_;
-                    if (i < k) J[r_ + size_t(c_) * ld] += rb[c_] * J[r_ + size_t(k) * ld];
-                    else J[r_ + size_t(c_) * ld] = rb[c_] * inv;
-                });
-            }
-        }
-        __syncthreads();
-    }
     for (int idx = tid; idx < nrc * n; idx += T) { // strict lower triangle := 0 (qpgen2 label 21)
         const int r = idx % nrc, c = idx / nrc;
         if (r0 + r > c) J[r + size_t(c) * ld] = 0.0;
     }
     __syncthreads();
+#ifdef GC_PROFILE
+    tp2 = clock64();
+#endif
     // ---- unconstrained minimiser x = J (J' (-c)): same exchange pattern as the iteration ------------------
     {
         for (int r = tid; r < nrc; r += T) W.a[r] = -P.c[r0 + r];
@@ -232,10 +345,16 @@ __device__ inline int gc_solve(const GiView& P, const GcLayout& L, GcWork& W, do
         cluster.sync();
     }
 
+#ifdef GC_PROFILE
+    tp3 = clock64();
+#endif
     int fail = 0, nact = 0, iter0 = 0, iter1 = 0;
     bool pending = false;
     int pc0 = 0;
     for (;;) {
+#ifdef GC_PROFILE
+        tmark = clock64();
+#endif
         ++iter0;
         if (iter0 > max_iter) { fail = 3; break; }
         // ================= alpha: pending rank-1 on my slab; slacks of my rows; candidate exchange ======
@@ -303,6 +422,9 @@ __device__ inline int gc_solve(const GiView& P, const GcLayout& L, GcWork& W, do
             }
         }
         cluster.sync();
+#ifdef GC_PROFILE
+        { const long long t = clock64(); ta += t - tmark; tmark = t; }
+#endif
         // ================= beta: select; d = J' a through reduce-scatter + all-gather ====================
         MinIdx sel; sel.v = 0.0; sel.i = -1;
         double s_nvl = 0.0, asign = -1.0;
@@ -351,6 +473,9 @@ __device__ inline int gc_solve(const GiView& P, const GcLayout& L, GcWork& W, do
                 }
                 cluster.sync();
             }
+#ifdef GC_PROFILE
+            { const long long t = clock64(); tb += t - tmark; tmark = t; }
+#endif
             // ============= gamma: z slab (all-gathered), r = S d1, candidates, norms =======================
             row_dots(J, ld, nrc, nact, n, W.d, W.w, W.part); // w temporarily holds my slab of z
             __syncthreads();
@@ -393,6 +518,9 @@ __device__ inline int gc_solve(const GiView& P, const GcLayout& L, GcWork& W, do
                 rc[4 * C + 2 * rank + 1] = za;
             }
             cluster.sync();
+#ifdef GC_PROFILE
+            { const long long t = clock64(); tg += t - tmark; tmark = t; }
+#endif
             // ============= delta: step lengths, x / u, reflection vectors ==================================
             zz = 0.0; za = 0.0;
             for (int k = 0; k < C; ++k) { zz += W.cand[4 * C + 2 * k]; za += W.cand[4 * C + 2 * k + 1]; }
@@ -529,6 +657,12 @@ __device__ inline int gc_solve(const GiView& P, const GcLayout& L, GcWork& W, do
         }
         if (fail != 0) break;
     }
+#ifdef GC_PROFILE
+    td = clock64() - tp3 - ta - tb - tg;
+    if (rank == 0 && tid == 0)
+        printf("GCPROF n=%d iters=%d load=%lld chol+inv=%lld x0=%lld alpha=%lld beta=%lld gamma=%lld delta+rest=%lld total=%lld\n", n, iter0, tp1 - tp0, tp2 - tp1,
+            tp3 - tp2, ta, tb, tg, td, clock64() - tp0);
+#endif
     __syncthreads();
     if (rank == 0) {
         if (O.x) for (int i = tid; i < n; i += T) O.x[i] = W.x[i];
