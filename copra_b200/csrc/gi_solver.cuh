@@ -23,6 +23,10 @@
 //     is the dropped row of S; J1 and S get rank-1 updates, the last column joins J2.
 #pragma once
 #include "common.cuh"
+#include "gi_factor.cuh"
+#ifdef GC_PROFILE
+#include <cstdio>
+#endif
 #include "engine.cuh"
 
 namespace cb {
@@ -67,21 +71,24 @@ __host__ __device__ inline GiLayout gi_layout(int n, int meq, int m, int threads
     L.oJ = o; if (j_smem) o += size_t(L.ldj) * n;
     L.oS = o; if (s_smem) o += size_t(L.lds) * n;
     L.oA = o; if (a_smem) o += size_t(L.lda) * n;
-    L.oX = o; o += n;
-    L.oD = o; o += n;
-    L.oZ = o; o += n;
     L.oAv = o; o += n;
-    L.oR = o; o += n;
     L.oU = o; o += n + 1;
-    L.oW = o; o += n;
-    L.oV = o; o += n;
-    L.oRow = o; o += n + 1;
     L.oNorm = o; o += meq + m;
     L.oLb = o; o += n;
     L.oUb = o; o += n;
+    L.oRed = o; o += 4 * kMaxWarps;
+    // the vectors below hold nothing while the factorisation runs: its panel / coefficient scratch aliases them (and
+    // extends past them when n is large)
+    L.oX = o; o += n;
+    L.oD = o; o += n;
+    L.oZ = o; o += n;
+    L.oR = o; o += n;
+    L.oW = o; o += n;
+    L.oV = o; o += n;
+    L.oRow = o; o += n + 1;
     L.oSl = o; o += meq + m;                    // products of the general rows with x
     L.oPart = o; o += 2 * size_t(threads) + 64; // partial sums of split dot products
-    L.oRed = o; o += 4 * kMaxWarps;
+    if (o < L.oX + gi_factor_scratch(n)) o = L.oX + gi_factor_scratch(n);
     size_t b = o * sizeof(double);
     L.oIact = b; b += sizeof(int) * size_t(n);
     L.oRowmap = b; b += sizeof(int) * size_t(n);
@@ -337,9 +344,14 @@ __device__ inline int gi_solve(const GiView& P, GiWork& W, const GiOut& O, doubl
     int fail = 0, nact = 0, iter0 = 0, iter1 = 0;
 
     // ---- 1. Cholesky Q = R'R (upper, in place) and 2. J = R^-1 in place ------------------------
-    if (!chol_upper_inplace(J, ld, n, W.row)) fail = 2;
+#ifdef GC_PROFILE
+    const long long gp0 = clock64();
+#endif
+    if (!gi_factor_blocked(J, ld, n, W.x)) fail = 2; // scratch: x d z r w v row sl part (gi_layout)
+#ifdef GC_PROFILE
+    const long long gp1 = clock64();
+#endif
     if (fail == 0) {
-        tri_inverse_upper_inplace(J, ld, n, W.row, W.z);
         // ---- 3. unconstrained minimiser x = J J' (-c) ---------------------------------------------
         col_dots(J, ld, n, 0, n, W.av, W.d);
         __syncthreads();
@@ -564,6 +576,9 @@ __device__ inline int gi_solve(const GiView& P, GiWork& W, const GiOut& O, doubl
     }
     __syncthreads();
     // ---- 6. results -------------------------------------------------------------------------------
+#ifdef GC_PROFILE
+    if (tid == 0 && blockIdx.x == 0) printf("GIPROF n=%d iters=%d factor=%lld rest=%lld\n", n, iter0, gp1 - gp0, clock64() - gp1);
+#endif
     if (O.x) for (int i = tid; i < n; i += T) O.x[i] = (fail == 2) ? 0.0 : W.x[i];
     if (O.iact) for (int i = tid; i < n; i += T) O.iact[i] = (i < nact) ? W.iact[i] : 0;
     if (tid == 0) {

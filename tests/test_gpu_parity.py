@@ -389,3 +389,28 @@ def test_small_solver_residency_variants(engine, monkeypatch):
             assert np.array_equal(r0["iters"], r1["iters"])
             assert np.allclose(r0["x"], r1["x"], rtol=1e-10, atol=1e-12)
         assert np.allclose(ref[1]["control"], mpc["control"], rtol=1e-9, atol=1e-9) and np.array_equal(ref[1]["iact"], mpc["iact"])
+
+
+@pytest.mark.parametrize("n,meq,m", [(65, 4, 40), (100, 0, 120), (131, 7, 90), (160, 3, 64), (203, 5, 150)])
+def test_mid_size_qps_general_and_cluster_kernels(engine, n, meq, m):
+    """64 < n: the general kernel (J in shared memory up to ~160 variables; blocked DMMA factorisation, gi_factor.cuh)
+    and, past one SM's shared memory, the cluster kernel -- random QPs with equalities, rows and bounds vs the oracle"""
+    rng = np.random.default_rng(1000 + n)
+    B = 3
+    L = rng.normal(size=(B, n, n))
+    Q = L @ np.swapaxes(L, 1, 2) / n + 0.5 * np.eye(n)
+    c = rng.normal(size=(B, n))
+    Aeq = rng.normal(size=(B, meq, n))
+    xf = rng.normal(size=(B, n))
+    beq = np.einsum("bij,bj->bi", Aeq, xf)
+    Aineq = rng.normal(size=(B, m, n))
+    bineq = np.einsum("bij,bj->bi", Aineq, xf) + rng.uniform(0.0, 1.0, size=(B, m))
+    lb = xf - rng.uniform(0.1, 2.0, size=(B, n))
+    ub = xf + rng.uniform(0.1, 2.0, size=(B, n))
+    r = engine.solve_qp_batch(Q, c, Aeq if meq else None, beq if meq else None, Aineq, bineq, lb, ub)
+    for b in range(B):
+        o = po.quadprog(Q[b], c[b], Aeq[b] if meq else None, beq[b] if meq else None, Aineq[b], bineq[b], lb[b], ub[b])
+        assert r["status"][b] == o["fail"] == 0
+        assert x_err(r["x"][b], o["x"]) < 1e-7, x_err(r["x"][b], o["x"])
+        assert active_set(r["iact"][b], r["nact"][b]) == active_set(o["iact"])
+        assert tuple(r["iters"][b]) == o["iter"]
