@@ -11,14 +11,15 @@ namespace cb {
 namespace {
 
 constexpr int kChains = 8;
-constexpr int kInner = 1024;
+constexpr int kInnerFma = 4096; // ~0.6 ms per launch
+constexpr int kInnerMma = 1024; // ~1.1 ms per launch
 
 __global__ void __launch_bounds__(256) dfma_chain_kernel(double* out, double a, double b)
 {
     double acc[kChains];
 #pragma unroll
     for (int i = 0; i < kChains; ++i) acc[i] = double(threadIdx.x + i);
-    for (int it = 0; it < kInner; ++it) {
+    for (int it = 0; it < kInnerFma; ++it) {
 #pragma unroll
         for (int i = 0; i < kChains; ++i) acc[i] = fma(acc[i], a, b);
     }
@@ -33,7 +34,7 @@ __global__ void __launch_bounds__(256) dmma_chain_kernel(double* out, double a, 
     double c0[kChains], c1[kChains];
 #pragma unroll
     for (int i = 0; i < kChains; ++i) { c0[i] = double(threadIdx.x); c1[i] = double(i); }
-    for (int it = 0; it < kInner; ++it) {
+    for (int it = 0; it < kInnerMma; ++it) {
 #pragma unroll
         for (int i = 0; i < kChains; ++i)
             asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -66,7 +67,7 @@ int fp64_peaks_measure(int sms, double* scratch, cudaStream_t st, double* dfma_t
             if ((e = cudaEventSynchronize(e1)) != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return -int(e); }
             float ms = 0.f;
             cudaEventElapsedTime(&ms, e0, e1);
-            const double per_thread = double(kInner) * kChains * (which == 0 ? 2.0 : 512.0 / 32.0);
+            const double per_thread = double(which == 0 ? kInnerFma : kInnerMma) * kChains * (which == 0 ? 2.0 : 512.0 / 32.0);
             const double tf = per_thread * double(grid) * threads / (double(ms) * 1e-3) * 1e-12;
             if (rep > 0 && tf > best[which]) best[which] = tf;
         }

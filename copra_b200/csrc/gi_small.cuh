@@ -298,6 +298,8 @@ __device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, do
 
     int fail = 0, nact = 0, iter0 = 0, iter1 = 0;
     // the padded diagonal entry (odd n) keeps the factorisation well defined; it is zeroed afterwards
+    // (the 8-pivot blocked DMMA factorisation of gi_factor.cuh was measured slower here: C2 2.03 vs 1.78 ms -- at n ~ 50 the
+    // per-pivot latency chain dominates, not the sweep)
     if (!gs_factor(J, ld, n, n2, W.row, W.rowk)) fail = 2;
     if (fail == 0) {
         if (n2 > n) {
