@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcopra_b200.so")
 
 HOST, DEVICE = 0, 1
+FLAG_NO_REG = 1  # COPRA_B200_FLAG_NO_REG: no 1e-6 I regulariser (single cost evaluation)
 COST_KINDS = {"trajectory": 0, "target": 1, "control": 2, "mixed": 3}
 CSTR_KINDS = {"trajectory": 0, "control": 1, "mixed": 2, "trajectory_bound": 3, "control_bound": 4}
 GET = dict(Phi=0, Psi=1, xi=2, Q=3, c=4, Aeq=5, beq=6, Aineq=7, bineq=8, lb=9, ub=10)

@@ -206,3 +206,25 @@ def test_facade_host_logic():
     r = subprocess.run([exe, "cpu"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "0 failures" in r.stdout
+
+
+def test_pycopra_autospan_and_system_checks_cpu():
+    """host-side pieces of the pyCopra-compatible front end need no GPU: AutoSpan (src/AutoSpan.cpp:10-48) and the
+    PreviewSystem dimension checks (src/PreviewSystem.cpp:27-49)"""
+    from copra_b200 import pycopra as copra
+    m = copra.AutoSpan.span_matrix(np.array([[1.0, 2.0]]), 3)
+    assert m.shape == (3, 6) and np.array_equal(m[1], [0, 0, 1, 2, 0, 0])
+    assert copra.AutoSpan.span_matrix(np.array([[1.0, 2.0]]), 2, 1).shape == (2, 6)  # one extra zero block column
+    assert np.array_equal(copra.AutoSpan.span_vector(np.array([1.0, 2.0]), 6), [1, 2, 1, 2, 1, 2])
+    with pytest.raises(RuntimeError):
+        copra.AutoSpan.span_matrix(np.ones((2, 2)), 5)
+    ps = copra.PreviewSystem()
+    with pytest.raises(RuntimeError):
+        ps.system(np.eye(2), np.ones((2, 1)), np.zeros(2), np.zeros(2), 0)
+    with pytest.raises(RuntimeError):
+        ps.system(np.eye(2), np.ones((3, 1)), np.zeros(2), np.zeros(2), 4)
+    ps.system(np.eye(2), np.ones((2, 1)), np.zeros(2), np.zeros(2), 4)
+    assert (ps.x_dim, ps.u_dim, ps.nr_x_Step, ps.full_x_dim, ps.full_u_dim) == (2, 1, 5, 10, 4) and not ps.is_updated
+    cost = copra.MixedCost(np.ones((1, 2)), np.ones((1, 1)), np.array([1.0, 2.0, 3.0]))
+    cost.auto_span()
+    assert cost._M.shape == (3, 8) and cost._N.shape == (3, 3) and cost._w.shape == (3,)
