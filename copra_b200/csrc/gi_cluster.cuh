@@ -174,6 +174,7 @@ __device__ inline int gc_solve(const GiView& P, const GcLayout& L, GcWork& W, do
                     const double akk = J[lr + size_t(p) * ld];
                     ok = ok && akk > 0.0;
                     const double rkk = ok ? sqrt(akk) : 1.0;
+                    __syncthreads(); // everyone has read the pivot before the thread that owns it overwrites it
                     for (int j = p + tid; j < n; j += T) {
                         const double v = (j == p) ? rkk : J[lr + size_t(j) * ld] / rkk;
                         J[lr + size_t(j) * ld] = v;
