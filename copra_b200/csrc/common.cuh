@@ -29,19 +29,26 @@ __device__ __forceinline__ MinIdx better(MinIdx a, MinIdx b)
     if (b.i >= 0 && (a.i < 0 || b.v < a.v || (b.v == a.v && b.i < a.i))) return b;
     return a;
 }
-// Warp arg-min: minimum value by a butterfly of fmin, then the lowest index among the lanes that hold
-// it through the redux unit (one instruction) -- same result as the pairwise `better` tournament.
+// Warp arg-min through the redux unit: the doubles are mapped to order-preserving 64-bit keys, the minimum key is
+// found with two 32-bit redux.min (high word, then low word among the lanes that tie on it) and the lowest index
+// among the lanes that hold it with a third -- same result as the pairwise `better` tournament (-0.0 is folded
+// into +0.0 first so that the key order agrees with IEEE '<' / '==').
 __device__ __forceinline__ MinIdx warp_argmin(MinIdx m)
 {
     const bool has = m.i >= 0;
-    double v = has ? m.v : CUDART_INF;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-    const unsigned idx = __reduce_min_sync(0xffffffffu, (has && m.v == v) ? unsigned(m.i) : 0xffffffffu);
+    unsigned long long u = (unsigned long long)__double_as_longlong(m.v + 0.0);
+    u = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+    const unsigned hi = has ? unsigned(u >> 32) : 0xffffffffu, lo = unsigned(u);
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    const bool c1 = has && hi == mh;
+    const unsigned ml = __reduce_min_sync(0xffffffffu, c1 ? lo : 0xffffffffu);
+    const unsigned idx = __reduce_min_sync(0xffffffffu, (c1 && lo == ml) ? unsigned(m.i) : 0xffffffffu);
     MinIdx r;
-    r.v = v;
-    r.i = (idx == 0xffffffffu) ? -1 : int(idx);
-    if (r.i < 0) r.v = 0.0;
+    if (idx == 0xffffffffu) { r.v = 0.0; r.i = -1; return r; }
+    unsigned long long k = ((unsigned long long)mh << 32) | ml;
+    k = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    r.v = __longlong_as_double((long long)k);
+    r.i = int(idx);
     return r;
 }
 
