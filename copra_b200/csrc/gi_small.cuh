@@ -437,8 +437,9 @@ __device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, do
                 if (tid >= nact && tid < n) { const double dj = W.d[tid]; dd = dj * dj; }
                 tc = warp_argmin(tc);
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    dd += __shfl_xor_sync(0xffffffffu, dd, o);
+                for (int o = 16; o > 0; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) { // zz / za live in lanes 0..7 only (zeros elsewhere): three steps reach lane 0
                     zz += __shfl_xor_sync(0xffffffffu, zz, o);
                     za += __shfl_xor_sync(0xffffffffu, za, o);
                 }
