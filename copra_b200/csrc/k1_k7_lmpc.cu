@@ -435,7 +435,9 @@ __global__ void k2_assemble_q_tiled_kernel(const __grid_constant__ BuildParams P
         o += F.rows;
     }
     const int tile = o;
-    for (int idx = threadIdx.x; idx < nU * nU; idx += blockDim.x) stage_sm[tile + idx] = (idx % nU == idx / nU) ? P.qdiag : 0.0;
+    for (int idx = threadIdx.x; idx < nU * nU; idx += blockDim.x) stage_sm[tile + idx] = 0.0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nU; i += blockDim.x) stage_sm[tile + i * (nU + 1)] = P.qdiag; // LMPC::updateSystem: Q = 1e-6 I
     __syncthreads();
     const int qstep = nu * (nU + 1);
     for (int t = threadIdx.x; t < N * nu * nu; t += blockDim.x) {
@@ -449,6 +451,15 @@ __global__ void k2_assemble_q_tiled_kernel(const __grid_constant__ BuildParams P
             const int r = F.rows, rnu = r * nu, i0 = F.i0, i1 = F.i1, wo = wto[ci];
             int ga = mgo[ci] + r * a, gb = mgo[ci] + r * (bb + nu * pidx);               // dd = pidx: o1 = 0, o2 = dd
             int qp = tile + ((N - 1) * nu + a) + ((N - 1 - pidx) * nu + bb) * nU;         // its entry at jmax = N-1
+            // sum_l (ga[l] * w[l]) * gb[l] in the reference order; straight-line code for the usual 1- and 2-row costs
+            auto wdot = [&](int oa, int ob) {
+                double sd = add_(0.0, mul_(mul_(stage_sm[oa], stage_sm[wo]), stage_sm[ob]));
+                if (r == 1) return sd;
+                sd = add_(sd, mul_(mul_(stage_sm[oa + 1], stage_sm[wo + 1]), stage_sm[ob + 1]));
+#pragma unroll 1
+                for (int l = 2; l < r; ++l) sd = add_(sd, mul_(mul_(stage_sm[oa + l], stage_sm[wo + l]), stage_sm[ob + l]));
+                return sd;
+            };
             double run = 0.0;
             int kk = 0, jmax = N - 1;
             for (int sidx = 0; sidx < N; ++sidx, --jmax, qp -= qstep) {
@@ -464,21 +475,13 @@ __global__ void k2_assemble_q_tiled_kernel(const __grid_constant__ BuildParams P
                 if (kk_hi < 0) continue;
                 double contrib;
                 if (i0 == 0) {
-                    for (; kk <= kk_hi; ++kk) {
-                        const int oa = ga + rnu * kk, ob = gb + rnu * kk;
-                        double sd = 0.0;
-                        for (int l = 0; l < r; ++l) sd = add_(sd, mul_(mul_(stage_sm[oa + l], stage_sm[wo + l]), stage_sm[ob + l]));
-                        run = add_(run, sd);
-                    }
+#pragma unroll 1 // one new term per step (two at the first step of an (N+1)-step cost): no unroll cascade
+                    for (; kk <= kk_hi; ++kk) run = add_(run, wdot(ga + rnu * kk, gb + rnu * kk));
                     contrib = run;
                 } else {
                     contrib = 0.0;
-                    for (int k2 = max(i0 - jmax, 0); k2 <= kk_hi; ++k2) {
-                        const int oa = ga + rnu * k2, ob = gb + rnu * k2;
-                        double sd = 0.0;
-                        for (int l = 0; l < r; ++l) sd = add_(sd, mul_(mul_(stage_sm[oa + l], stage_sm[wo + l]), stage_sm[ob + l]));
-                        contrib = add_(contrib, sd);
-                    }
+#pragma unroll 1
+                    for (int k2 = max(i0 - jmax, 0); k2 <= kk_hi; ++k2) contrib = add_(contrib, wdot(ga + rnu * k2, gb + rnu * k2));
                 }
                 stage_sm[qp] = add_(stage_sm[qp], contrib);
             }
