@@ -865,8 +865,14 @@ __global__ void k7_results_kernel(const __grid_constant__ BuildParams P, const d
     for (int a = 0; a < nx; ++a) s1 = add_(s1, mul_(Phi[row + (long long)a * X], P.initial_state ? xr[a] : P.x0.at(b)[a]));
     double s2 = 0.0;
     int go = (i - 1) * nx + r; // G_{i-1-j}[r, :]
-    for (int j = 0; j < i; ++j, go -= nx)
-        for (int cc = 0; cc < nu; ++cc) s2 = add_(s2, mul_(Gs[go + cc * NX], xr[off + j * nu + cc]));
+    if (nu == 1) { // the common single-input case without the inner-loop bookkeeping
+        for (int j = 0; j < i; ++j, go -= nx) s2 = add_(s2, mul_(Gs[go], xr[off + j]));
+    } else {
+        for (int j = 0; j < i; ++j, go -= nx) {
+#pragma unroll 1
+            for (int cc = 0; cc < nu; ++cc) s2 = add_(s2, mul_(Gs[go + cc * NX], xr[off + j * nu + cc]));
+        }
+    }
     traj[(long long)b * X + row] = add_(add_(s1, s2), P.xi[(long long)b * X + row]);
 }
 
