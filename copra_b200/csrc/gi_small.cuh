@@ -82,6 +82,14 @@ __device__ inline GsWork gs_carve(const GsLayout& L, unsigned char* smem)
     return W;
 }
 
+// Ampere-style asynchronous 8-byte copy global -> shared (no register staging, any number in flight per thread)
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
 
@@ -263,22 +271,21 @@ __device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, do
     int* redi = W.redi;
 
     // ---- 0. load (zero padded) ---------------------------------------------------------------------
-    // flat sweeps: the index division costs instructions but lets the compiler keep many independent loads in flight per
-    // thread (a warp-per-column nest and incremental indices were both measured slower on C2: 1.78 / 1.74 vs 1.72 ms)
+    // Q and the general rows stream in with cp.async (no register staging, every copy of a thread in flight at once); the
+    // factorisation starts as soon as Q has landed, the rows are only awaited before their norms are needed
     for (int idx = tid; idx < ld * n2; idx += kSmT) {
         const int i = idx % ld, j = idx / ld;
-        J[idx] = (i < n && j < n) ? P.Q[i + size_t(j) * n] : ((i == j && i < n2) ? 1.0 : 0.0);
+        if (i < n && j < n) cp_async8(J + idx, P.Q + i + size_t(j) * n);
+        else J[idx] = (i == j && i < n2) ? 1.0 : 0.0;
     }
+    cp_async_commit();
     if (mg > 0) {
         if (!AG)
             for (int idx = tid; idx < lda * n2; idx += kSmT) {
                 const int i = idx % lda, k = idx / lda;
-                double v = 0.0;
-                if (k < n) {
-                    if (i < meq) v = P.Aeq[i + size_t(k) * meq];
-                    else if (i < mg) v = P.Aineq[(i - meq) + size_t(k) * m];
-                }
-                A[idx] = v;
+                if (k < n && i < meq) cp_async8(A + idx, P.Aeq + i + size_t(k) * meq);
+                else if (k < n && i < mg) cp_async8(A + idx, P.Aineq + (i - meq) + size_t(k) * m);
+                else A[idx] = 0.0;
             }
         for (int i = tid; i < mg2; i += kSmT) W.bg[i] = (i < meq) ? P.beq[i] : (i < mg ? P.bineq[i - meq] : 0.0);
     }
@@ -294,13 +301,17 @@ __device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, do
     if (tid < 2) W.u[n2 + tid] = 0.0;
     for (int i = tid; i < q; i += kSmT) W.active[i] = 0;
     for (int i = tid; i < meq; i += kSmT) W.sgn[i] = 1;
-    __syncthreads();
+    cp_async_commit();   // group 1: the general rows (possibly empty)
+    cp_async_wait<1>();  // group 0 (Q) has landed for this thread ...
+    __syncthreads();     // ... and for everyone
 
     int fail = 0, nact = 0, iter0 = 0, iter1 = 0;
     // the padded diagonal entry (odd n) keeps the factorisation well defined; it is zeroed afterwards
     // (the 8-pivot blocked DMMA factorisation of gi_factor.cuh was measured slower here: C2 2.03 vs 1.78 ms -- at n ~ 50 the
     // per-pivot latency chain dominates, not the sweep)
     if (!gs_factor(J, ld, n, n2, W.row, W.rowk)) fail = 2;
+    cp_async_wait<0>(); // the general rows have landed (also drains the copies before the buffers are reused)
+    __syncthreads();
     if (fail == 0) {
         if (n2 > n) {
             for (int i = tid; i < n2; i += kSmT) { J[n + size_t(i) * ld] = 0.0; J[i + size_t(n) * ld] = 0.0; }
