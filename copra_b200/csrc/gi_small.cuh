@@ -194,6 +194,83 @@ __device__ __forceinline__ void gs_rank1(double* __restrict__ M, int ld, int np,
 //     J[i,j] = (i == k ? 0 : J[i,j]) + mult[j] * coef[i],   i <= j,  j > k
 // with mult[j] = R[k,j], coef[i] = -J[i,k]/R[k,k] (i < k), 1/R[k,k] (i == k), -R[k,i] (i > k).  Every entry sees
 // its updates in LINPACK's order; two block barriers per k.  128 threads, lane = row pair, warp = column group.
+// Two pivots per pass (gs_factor2): the sweep of pivot k+1 only needs row k+1 and column k+1 as pivot k leaves them, and
+// every thread can form its own entries of those from pre-pass values -- so both rank-1 sweeps are applied to each entry in
+// one visit (same operands, same order as two single passes), halving the barriers and the load/store traffic.
+__device__ inline bool gs_factor2(double* __restrict__ J, int ld, int n, int n2, double* __restrict__ coef1, double* __restrict__ mult1,
+    double* __restrict__ coef2, double* __restrict__ mult2)
+{
+    const int tid = threadIdx.x, lane = lane_id(), g = tid >> 5;
+    int k = 0;
+    for (; k + 1 < n; k += 2) {
+        const double akk = J[k + size_t(k) * ld];
+        if (!(akk > 0.0)) return false;
+        const double rkk = sqrt(akk), inv = 1.0 / rkk;
+        const double mk1 = J[k + size_t(k + 1) * ld] / rkk;                   // R[k,k+1]
+        const double a2 = fma(mk1, -mk1, J[(k + 1) + size_t(k + 1) * ld]);     // pivot k+1 after pass k
+        if (!(a2 > 0.0)) return false;
+        const double r2 = sqrt(a2), inv2 = 1.0 / r2;
+        if (tid < n2) {
+            double c1, c2;
+            if (tid < k) {
+                c1 = J[tid + size_t(k) * ld] * (-inv);
+                c2 = fma(mk1, c1, J[tid + size_t(k + 1) * ld]) * (-inv2);
+            } else if (tid == k) {
+                c1 = inv;
+                c2 = fma(mk1, inv, 0.0) * (-inv2);
+            } else if (tid == k + 1) {
+                mult1[tid] = mk1;
+                c1 = -mk1;
+                c2 = inv2;
+            } else if (tid < n) {
+                const double m1 = J[k + size_t(tid) * ld] / rkk;
+                const double m2 = fma(m1, -mk1, J[(k + 1) + size_t(tid) * ld]) / r2;
+                mult1[tid] = m1;
+                mult2[tid] = m2;
+                c1 = -m1;
+                c2 = -m2;
+            } else { c1 = 0.0; c2 = 0.0; } // pad row of an odd n
+            coef1[tid] = c1;
+            coef2[tid] = c2;
+        }
+        __syncthreads();
+        if (tid <= k) J[tid + size_t(k) * ld] = coef1[tid];         // columns k and k+1 of the inverse
+        if (tid <= k + 1) J[tid + size_t(k + 1) * ld] = coef2[tid];
+        {
+            const int i0 = 2 * lane, i1 = i0 + 1;
+            if (i0 < n) {
+                const double2 c1 = ld2(coef1 + i0), c2 = ld2(coef2 + i0);
+                for (int j = max(k + 2, i0) + ((g - max(k + 2, i0)) & 3); j < n; j += 4) {
+                    double2 a = ld2(J + i0 + size_t(j) * ld);
+                    const double m1 = mult1[j], m2 = mult2[j];
+                    a.x = fma(m1, c1.x, (i0 == k) ? 0.0 : a.x);
+                    a.x = fma(m2, c2.x, (i0 == k + 1) ? 0.0 : a.x);
+                    if (i1 <= j) {
+                        a.y = fma(m1, c1.y, (i1 == k) ? 0.0 : a.y);
+                        a.y = fma(m2, c2.y, (i1 == k + 1) ? 0.0 : a.y);
+                    }
+                    *reinterpret_cast<double2*>(J + i0 + size_t(j) * ld) = a;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (k < n) { // odd n: the last pivot alone
+        const double akk = J[k + size_t(k) * ld];
+        if (!(akk > 0.0)) return false;
+        const double inv = 1.0 / sqrt(akk);
+        __syncthreads();
+        if (tid < k) J[tid + size_t(k) * ld] *= -inv;
+        else if (tid == k) J[k + size_t(k) * ld] = inv;
+        __syncthreads();
+    }
+    // strict lower triangle := 0 (qpgen2 label 21); pad row/column are zeroed by the caller
+    for (int j = g; j < n2; j += kSmT / 32)
+        for (int i = j + 1 + lane; i < n2; i += 32) J[i + size_t(j) * ld] = 0.0;
+    __syncthreads();
+    return true;
+}
+
 __device__ inline bool gs_factor(double* __restrict__ J, int ld, int n, int n2, double* __restrict__ coef, double* __restrict__ mult)
 {
     const int tid = threadIdx.x, lane = lane_id(), g = tid >> 5;
@@ -309,7 +386,7 @@ __device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, do
     // the padded diagonal entry (odd n) keeps the factorisation well defined; it is zeroed afterwards
     // (the 8-pivot blocked DMMA factorisation of gi_factor.cuh was measured slower here: C2 2.03 vs 1.78 ms -- at n ~ 50 the
     // per-pivot latency chain dominates, not the sweep)
-    if (!gs_factor(J, ld, n, n2, W.row, W.rowk)) fail = 2;
+    if (!gs_factor2(J, ld, n, n2, W.row, W.rowk, W.z, W.d)) fail = 2; // z, d hold nothing yet
     cp_async_wait<0>(); // the general rows have landed (also drains the copies before the buffers are reused)
     __syncthreads();
     if (fail == 0) {
