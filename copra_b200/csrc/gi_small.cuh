@@ -193,8 +193,8 @@ __device__ __forceinline__ void gs_rank1(double* __restrict__ M, int ld, int np,
 // disjoint entries (rows > k vs rows <= k of the columns j > k), so both are ONE rank-1 sweep
 //     J[i,j] = (i == k ? 0 : J[i,j]) + mult[j] * coef[i],   i <= j,  j > k
 // with mult[j] = R[k,j], coef[i] = -J[i,k]/R[k,k] (i < k), 1/R[k,k] (i == k), -R[k,i] (i > k).  Every entry sees
-// its updates in LINPACK's order; two block barriers per k.  128 threads, lane = row pair, warp = column group.
-// Two pivots per pass (gs_factor2): the sweep of pivot k+1 only needs row k+1 and column k+1 as pivot k leaves them, and
+// its updates in LINPACK's order.  128 threads, lane = row pair, warp = column group.
+// Two pivots per pass (gs_factor2, two block barriers per pair): the sweep of pivot k+1 only needs row k+1 and column k+1 as pivot k leaves them, and
 // every thread can form its own entries of those from pre-pass values -- so both rank-1 sweeps are applied to each entry in
 // one visit (same operands, same order as two single passes), halving the barriers and the load/store traffic.
 __device__ inline bool gs_factor2(double* __restrict__ J, int ld, int n, int n2, double* __restrict__ coef1, double* __restrict__ mult1,
@@ -263,63 +263,6 @@ __device__ inline bool gs_factor2(double* __restrict__ J, int ld, int n, int n2,
         if (tid < k) J[tid + size_t(k) * ld] *= -inv;
         else if (tid == k) J[k + size_t(k) * ld] = inv;
         __syncthreads();
-    }
-    // strict lower triangle := 0 (qpgen2 label 21); pad row/column are zeroed by the caller
-    for (int j = g; j < n2; j += kSmT / 32)
-        for (int i = j + 1 + lane; i < n2; i += 32) J[i + size_t(j) * ld] = 0.0;
-    __syncthreads();
-    return true;
-}
-
-__device__ inline bool gs_factor(double* __restrict__ J, int ld, int n, int n2, double* __restrict__ coef, double* __restrict__ mult)
-{
-    const int tid = threadIdx.x, lane = lane_id(), g = tid >> 5;
-    double akk = J[0];
-    if (!(akk > 0.0)) return false;
-    double rkk = sqrt(akk), inv = 1.0 / rkk;
-    for (int k = 0; k < n; ++k) {
-        // the next pivot before this step's sweep touches it (nobody writes J until the barrier)
-        const double anext = (k + 1 < n) ? J[(k + 1) + size_t(k + 1) * ld] : 1.0;
-        if (tid < n2) {
-            double c;
-            if (tid < k) c = J[tid + size_t(k) * ld] * (-inv);
-            else if (tid == k) c = inv;
-            else if (tid < n) {
-                const double mj = J[k + size_t(tid) * ld] / rkk;
-                mult[tid] = mj;
-                c = -mj;
-            } else c = 0.0; // pad row of an odd n
-            coef[tid] = c;
-        }
-        __syncthreads();
-        // pivot k+1 after this step's update, computed by every thread exactly as the sweep computes it; its square
-        // root and reciprocal (two long dependent chains) are issued here and overlap with the sweep below
-        double rnext = 1.0, inext = 1.0;
-        bool pd = true;
-        if (k + 1 < n) {
-            const double a2 = fma(mult[k + 1], coef[k + 1], anext);
-            pd = a2 > 0.0;
-            rnext = sqrt(a2);
-            inext = 1.0 / rnext;
-        }
-        if (tid <= k) J[tid + size_t(k) * ld] = coef[tid]; // column k of the inverse (dpori), diagonal = 1/R[k,k]
-        {
-            const int i0 = 2 * lane, i1 = i0 + 1;
-            if (i0 < n) {
-                const double2 c = ld2(coef + i0);
-                for (int j = max(k + 1, i0) + ((g - max(k + 1, i0)) & 3); j < n; j += 4) {
-                    double2 a = ld2(J + i0 + size_t(j) * ld);
-                    const double mj = mult[j];
-                    a.x = fma(mj, c.x, (i0 == k) ? 0.0 : a.x);
-                    if (i1 <= j) a.y = fma(mj, c.y, (i1 == k) ? 0.0 : a.y);
-                    *reinterpret_cast<double2*>(J + i0 + size_t(j) * ld) = a;
-                }
-            }
-        }
-        __syncthreads();
-        if (!pd) return false;
-        rkk = rnext;
-        inv = inext;
     }
     // strict lower triangle := 0 (qpgen2 label 21); pad row/column are zeroed by the caller
     for (int j = g; j < n2; j += kSmT / 32)
