@@ -194,77 +194,123 @@ __device__ __forceinline__ void gs_rank1(double* __restrict__ M, int ld, int np,
 //     J[i,j] = (i == k ? 0 : J[i,j]) + mult[j] * coef[i],   i <= j,  j > k
 // with mult[j] = R[k,j], coef[i] = -J[i,k]/R[k,k] (i < k), 1/R[k,k] (i == k), -R[k,i] (i > k).  Every entry sees
 // its updates in LINPACK's order.  128 threads, lane = row pair, warp = column group.
-// Two pivots per pass (gs_factor2, two block barriers per pair): the sweep of pivot k+1 only needs row k+1 and column k+1 as pivot k leaves them, and
-// every thread can form its own entries of those from pre-pass values -- so both rank-1 sweeps are applied to each entry in
-// one visit (same operands, same order as two single passes), halving the barriers and the load/store traffic.
-__device__ inline bool gs_factor2(double* __restrict__ J, int ld, int n, int n2, double* __restrict__ coef1, double* __restrict__ mult1,
-    double* __restrict__ coef2, double* __restrict__ mult2)
+//
+// NB pivots per pass (two block barriers per pass): the sweeps of the later pivots of a pass only need the block's rows and
+// columns as the earlier pivots leave them, and every thread can form its own entries of those from pre-pass values -- the
+// NB x NB diagonal block is factored redundantly in registers, each thread folds its NB coefficients / multipliers, and all
+// NB rank-1 sweeps are applied to each entry in one visit (same operands, same order as NB single passes).  That divides the
+// barriers and the shared-memory traffic of the factorisation by NB.
+template <int NB>
+__device__ __forceinline__ bool gs_factor_pass(double* __restrict__ J, int ld, int n, int n2, int k, double* const* coefp, double* const* multp)
 {
     const int tid = threadIdx.x, lane = lane_id(), g = tid >> 5;
-    int k = 0;
-    for (; k + 1 < n; k += 2) {
-        const double akk = J[k + size_t(k) * ld];
-        if (!(akk > 0.0)) return false;
-        const double rkk = sqrt(akk), inv = 1.0 / rkk;
-        const double mk1 = J[k + size_t(k + 1) * ld] / rkk;                   // R[k,k+1]
-        const double a2 = fma(mk1, -mk1, J[(k + 1) + size_t(k + 1) * ld]);     // pivot k+1 after pass k
-        if (!(a2 > 0.0)) return false;
-        const double r2 = sqrt(a2), inv2 = 1.0 / r2;
-        if (tid < n2) {
-            double c1, c2;
-            if (tid < k) {
-                c1 = J[tid + size_t(k) * ld] * (-inv);
-                c2 = fma(mk1, c1, J[tid + size_t(k + 1) * ld]) * (-inv2);
-            } else if (tid == k) {
-                c1 = inv;
-                c2 = fma(mk1, inv, 0.0) * (-inv2);
-            } else if (tid == k + 1) {
-                mult1[tid] = mk1;
-                c1 = -mk1;
-                c2 = inv2;
-            } else if (tid < n) {
-                const double m1 = J[k + size_t(tid) * ld] / rkk;
-                const double m2 = fma(m1, -mk1, J[(k + 1) + size_t(tid) * ld]) / r2;
-                mult1[tid] = m1;
-                mult2[tid] = m2;
-                c1 = -m1;
-                c2 = -m2;
-            } else { c1 = 0.0; c2 = 0.0; } // pad row of an odd n
-            coef1[tid] = c1;
-            coef2[tid] = c2;
+    // ---- the diagonal block, redundantly in every thread (broadcast loads of pre-pass values) -----------------------------
+    double R[NB][NB], rk[NB], inv[NB];
+    bool pd = true;
+#pragma unroll
+    for (int p = 0; p < NB; ++p) {
+        double dg = J[(k + p) + size_t(k + p) * ld];
+#pragma unroll
+        for (int q = 0; q < p; ++q) dg = fma(R[q][p], -R[q][p], dg);
+        pd = pd && dg > 0.0;
+        rk[p] = sqrt(dg);
+        inv[p] = 1.0 / rk[p];
+#pragma unroll
+        for (int c = p + 1; c < NB; ++c) {
+            double v = J[(k + p) + size_t(k + c) * ld];
+#pragma unroll
+            for (int q = 0; q < p; ++q) v = fma(R[q][c], -R[q][p], v);
+            R[p][c] = v / rk[p];
         }
-        __syncthreads();
-        if (tid <= k) J[tid + size_t(k) * ld] = coef1[tid];         // columns k and k+1 of the inverse
-        if (tid <= k + 1) J[tid + size_t(k + 1) * ld] = coef2[tid];
-        {
-            const int i0 = 2 * lane, i1 = i0 + 1;
-            if (i0 < n) {
-                const double2 c1 = ld2(coef1 + i0), c2 = ld2(coef2 + i0);
-                for (int j = max(k + 2, i0) + ((g - max(k + 2, i0)) & 3); j < n; j += 4) {
-                    double2 a = ld2(J + i0 + size_t(j) * ld);
-                    const double m1 = mult1[j], m2 = mult2[j];
-                    a.x = fma(m1, c1.x, (i0 == k) ? 0.0 : a.x);
-                    a.x = fma(m2, c2.x, (i0 == k + 1) ? 0.0 : a.x);
-                    if (i1 <= j) {
-                        a.y = fma(m1, c1.y, (i1 == k) ? 0.0 : a.y);
-                        a.y = fma(m2, c2.y, (i1 == k + 1) ? 0.0 : a.y);
+    }
+    if (!pd) return false; // uniform: every thread computed the same values
+    // ---- this thread's row / column of the block ---------------------------------------------------------------------------
+    double cf[NB], mu[NB];
+#pragma unroll
+    for (int p = 0; p < NB; ++p) { cf[p] = 0.0; mu[p] = 0.0; }
+    if (tid < n) {
+        if (tid >= k + NB) { // column tid of the block rows: R[k+p, tid]
+#pragma unroll
+            for (int p = 0; p < NB; ++p) {
+                double v = J[(k + p) + size_t(tid) * ld];
+#pragma unroll
+                for (int q = 0; q < p; ++q) v = fma(mu[q], -R[q][p], v);
+                mu[p] = v / rk[p];
+                cf[p] = -mu[p];
+            }
+        } else if (tid < k) { // row tid of the block columns
+#pragma unroll
+            for (int p = 0; p < NB; ++p) {
+                double v = J[tid + size_t(k + p) * ld];
+#pragma unroll
+                for (int q = 0; q < p; ++q) v = fma(R[q][p], cf[q], v);
+                cf[p] = v * (-inv[p]);
+            }
+        } else { // a block row t = tid - k: below the pivots p < t, the pivot itself at p == t, above the pivots p > t
+#pragma unroll
+            for (int t = 0; t < NB; ++t) { // compile-time t: everything stays in registers
+                if (tid != k + t) continue;
+#pragma unroll
+                for (int p = 0; p < NB; ++p) {
+                    if (p < t) { mu[p] = R[p][t]; cf[p] = -mu[p]; }
+                    else if (p == t) cf[p] = inv[p];
+                    else {
+                        double v = 0.0; // pivot t zeroed this row first
+#pragma unroll
+                        for (int q = t; q < p; ++q) v = fma(R[q][p], cf[q], v);
+                        cf[p] = v * (-inv[p]);
                     }
-                    *reinterpret_cast<double2*>(J + i0 + size_t(j) * ld) = a;
                 }
             }
         }
-        __syncthreads();
     }
-    if (k < n) { // odd n: the last pivot alone
-        const double akk = J[k + size_t(k) * ld];
-        if (!(akk > 0.0)) return false;
-        const double inv = 1.0 / sqrt(akk);
-        __syncthreads();
-        if (tid < k) J[tid + size_t(k) * ld] *= -inv;
-        else if (tid == k) J[k + size_t(k) * ld] = inv;
-        __syncthreads();
+    if (tid < n2) {
+#pragma unroll
+        for (int p = 0; p < NB; ++p) { coefp[p][tid] = cf[p]; multp[p][tid] = mu[p]; }
     }
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < NB; ++p)
+        if (tid <= k + p) J[tid + size_t(k + p) * ld] = cf[p]; // the finished columns of the inverse
+    {
+        const int i0 = 2 * lane, i1 = i0 + 1, j0 = k + NB;
+        if (i0 < n) {
+            double2 c[NB];
+#pragma unroll
+            for (int p = 0; p < NB; ++p) c[p] = ld2(coefp[p] + i0);
+            for (int j = max(j0, i0) + ((g - max(j0, i0)) & 3); j < n; j += 4) {
+                double2 a = ld2(J + i0 + size_t(j) * ld);
+                const bool second = i1 <= j;
+#pragma unroll
+                for (int p = 0; p < NB; ++p) {
+                    const double m = multp[p][j];
+                    a.x = fma(m, c[p].x, (i0 == k + p) ? 0.0 : a.x);
+                    if (second) a.y = fma(m, c[p].y, (i1 == k + p) ? 0.0 : a.y);
+                }
+                *reinterpret_cast<double2*>(J + i0 + size_t(j) * ld) = a;
+            }
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
+// coefp / multp: NB + NB scratch vectors of n2 doubles (16-byte aligned).  NB = 2 and NB = 4 measure the same on C2 / C4
+// (1.59 / 5.99 ms: the longer redundant prelude of NB = 4 eats what its fewer barriers save); callers use kSmFacNB.
+constexpr int kSmFacNB = 2;
+template <int NB>
+__device__ inline bool gs_factor_nb(double* __restrict__ J, int ld, int n, int n2, double* const* coefp, double* const* multp)
+{
+    int k = 0;
+    for (; k + NB <= n; k += NB)
+        if (!gs_factor_pass<NB>(J, ld, n, n2, k, coefp, multp)) return false;
+    if (NB > 2 && k + 2 <= n) {
+        if (!gs_factor_pass<2>(J, ld, n, n2, k, coefp, multp)) return false;
+        k += 2;
+    }
+    if (k < n && !gs_factor_pass<1>(J, ld, n, n2, k, coefp, multp)) return false;
     // strict lower triangle := 0 (qpgen2 label 21); pad row/column are zeroed by the caller
+    const int lane = lane_id(), g = threadIdx.x >> 5;
     for (int j = g; j < n2; j += kSmT / 32)
         for (int i = j + 1 + lane; i < n2; i += 32) J[i + size_t(j) * ld] = 0.0;
     __syncthreads();
@@ -329,7 +375,11 @@ __device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, do
     // the padded diagonal entry (odd n) keeps the factorisation well defined; it is zeroed afterwards
     // (the 8-pivot blocked DMMA factorisation of gi_factor.cuh was measured slower here: C2 2.03 vs 1.78 ms -- at n ~ 50 the
     // per-pivot latency chain dominates, not the sweep)
-    if (!gs_factor2(J, ld, n, n2, W.row, W.rowk, W.z, W.d)) fail = 2; // z, d hold nothing yet
+    {   // scratch of the factorisation: vectors that hold nothing yet (red has 64 entries >= n2)
+        double* const coefp[4] = { W.x, W.d, W.z, W.w };
+        double* const multp[4] = { W.row, W.rowk, W.r, W.red };
+        if (!gs_factor_nb<kSmFacNB>(J, ld, n, n2, coefp, multp)) fail = 2;
+    }
     cp_async_wait<0>(); // the general rows have landed (also drains the copies before the buffers are reused)
     __syncthreads();
     if (fail == 0) {

@@ -803,10 +803,7 @@ __global__ void __launch_bounds__(kSmT, 4) k4_schur_small_kernel(const __grid_co
     const int tid = threadIdx.x;
     double* Jm = sm;                       // ld x n2
     double* coef = Jm + (size_t)ld * n2;   // n2 + 2
-    double* mult = coef + n2 + 2;          // n2
-    double* coef2 = mult + n2;             // n2 + 2   (second pivot of a pass, gs_factor2)
-    double* mult2 = coef2 + n2 + 2;        // n2
-    double* V = mult2 + n2;                // nx x nU
+    double* V = coef + 8 * (size_t)(n2 + 2); // nx x nU   (8 scratch vectors of n2 + 2: coefficients / multipliers of 4 pivots)
     for (int b = blockIdx.x; b < P.batch; b += gridDim.x) {
         double* Q = P.Q + (long long)b * nvar * nvar;
         __syncthreads();
@@ -815,7 +812,9 @@ __global__ void __launch_bounds__(kSmT, 4) k4_schur_small_kernel(const __grid_co
             Jm[idx] = (i < nU && j < nU) ? Q[(nx + i) + (long long)(nx + j) * nvar] : ((i == j && i < n2) ? 1.0 : 0.0);
         }
         __syncthreads();
-        const bool ok = gs_factor2(Jm, ld, nU, n2, coef, mult, coef2, mult2);
+        double* const coefp[4] = { coef, coef + (n2 + 2), coef + 2 * (n2 + 2), coef + 3 * (n2 + 2) };
+        double* const multp[4] = { coef + 4 * (n2 + 2), coef + 5 * (n2 + 2), coef + 6 * (n2 + 2), coef + 7 * (n2 + 2) };
+        const bool ok = gs_factor_nb<kSmFacNB>(Jm, ld, nU, n2, coefp, multp);
         if (ok) {
             for (int t = tid; t < nx * nU; t += kSmT) { // V[s,i] = sum_{k<=i} E[s,k] J[k,i]
                 const int s = t % nx, i = t / nx;
@@ -981,7 +980,7 @@ int k2k4_assemble_launch(const BuildParams& P, double* schur_ws, long long schur
     CB_CHECK_LAUNCH();
     if (P.initial_state && P.nU <= kSmMaxN) {
         const int n2 = (P.nU + 1) & ~1;
-        const size_t smem = sizeof(double) * (size_t(ld_vec2(P.nU)) * n2 + 4 * size_t(n2) + 4 + size_t(P.nx) * P.nU);
+        const size_t smem = sizeof(double) * (size_t(ld_vec2(P.nU)) * n2 + 8 * (size_t(n2) + 2) + size_t(P.nx) * P.nU);
         if (smem + 1024 > smem_optin) return -int(cudaErrorInvalidValue);
         cudaError_t e = cudaFuncSetAttribute(k4_schur_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) return -int(e);
