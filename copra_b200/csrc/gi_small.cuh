@@ -402,7 +402,7 @@ __device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, do
         for (int i = tid; i < mg; i += kSmT) {
             double s = 0.0;
             for (int k = 0; k < n; ++k) { const double v = AG ? ag(i, k) : A[i + size_t(k) * lda]; s += v * v; }
-            W.norm[i] = sqrt(s);
+            W.norm[i] = 1.0 / sqrt(s); // reciprocal norm: the per-iteration normalisation is a multiply
         }
         __syncthreads();
 
@@ -423,8 +423,7 @@ __device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, do
                 }
                 if (W.active[i]) s = 0.0;
                 if (s < 0.0) {
-                    const double nrm = (i < mg) ? W.norm[i] : 1.0;
-                    MinIdx c; c.v = s / nrm; c.i = i;
+                    MinIdx c; c.v = (i < mg) ? s * W.norm[i] : s; c.i = i; // bound rows have unit normals
                     const MinIdx nb = better(best, c);
                     if (nb.i != best.i) best_s = s;
                     best = nb;
