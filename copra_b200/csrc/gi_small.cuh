@@ -560,12 +560,13 @@ __device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, do
                             W.v[tid] = (tid == nact) ? d0 - delta : W.d[tid];
                         }
                         const int newrow = W.rowmap[nact];
+                        const double invd = 1.0 / delta; // one division for the whole new column of S = R^-1
                         if (tid < nact) {
-                            S[W.rowmap[tid] + size_t(nact) * lds] = -W.r[tid] / delta;
+                            S[W.rowmap[tid] + size_t(nact) * lds] = -W.r[tid] * invd;
                             S[newrow + size_t(tid) * lds] = 0.0;
                         }
                         if (tid == 0) {
-                            S[newrow + size_t(nact) * lds] = 1.0 / delta;
+                            S[newrow + size_t(nact) * lds] = invd;
                             W.iact[nact] = nvl + 1;
                             W.active[nvl] = 1;
                         }
