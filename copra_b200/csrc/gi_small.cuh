@@ -552,7 +552,10 @@ __device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, do
                     if (t2min) {
                         // ---- ADD: H d2 = delta e1 ; w = tau (z - delta J[:,nact]) ; v = d2 - delta e1 -----
                         const double d0 = W.d[nact];
-                        const double sigma = sqrt(dd);
+                        // sigma = |d2| and 1/sigma from one reciprocal square root (the reflection only needs them to rounding:
+                        // any tau, delta pair consistent to a few ulp keeps J orthogonal to rounding like the update itself)
+                        const double rsig = rsqrt(dd);
+                        const double sigma = dd * rsig;
                         const double delta = (d0 >= 0.0) ? -sigma : sigma;
                         const double tau = 1.0 / (sigma * (sigma + fabs(d0)));
                         if (tid < n2) {
@@ -560,7 +563,7 @@ __device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, do
                             W.v[tid] = (tid == nact) ? d0 - delta : W.d[tid];
                         }
                         const int newrow = W.rowmap[nact];
-                        const double invd = 1.0 / delta; // one division for the whole new column of S = R^-1
+                        const double invd = (d0 >= 0.0) ? -rsig : rsig; // 1 / delta
                         if (tid < nact) {
                             S[W.rowmap[tid] + size_t(nact) * lds] = -W.r[tid] * invd;
                             S[newrow + size_t(tid) * lds] = 0.0;
