@@ -205,7 +205,7 @@ __device__ __forceinline__ bool gs_factor_pass(double* __restrict__ J, int ld, i
 {
     const int tid = threadIdx.x, lane = lane_id(), g = tid >> 5;
     // ---- the diagonal block, redundantly in every thread (broadcast loads of pre-pass values) -----------------------------
-    double R[NB][NB], rk[NB], inv[NB];
+    double R[NB][NB], inv[NB];
     bool pd = true;
 #pragma unroll
     for (int p = 0; p < NB; ++p) {
@@ -213,14 +213,13 @@ __device__ __forceinline__ bool gs_factor_pass(double* __restrict__ J, int ld, i
 #pragma unroll
         for (int q = 0; q < p; ++q) dg = fma(R[q][p], -R[q][p], dg);
         pd = pd && dg > 0.0;
-        rk[p] = sqrt(dg);
-        inv[p] = 1.0 / rk[p];
+        inv[p] = rsqrt(dg); // 1 / R[p,p]; rows are scaled by multiplying with it (LINPACK divides by sqrt: same to rounding)
 #pragma unroll
         for (int c = p + 1; c < NB; ++c) {
             double v = J[(k + p) + size_t(k + c) * ld];
 #pragma unroll
             for (int q = 0; q < p; ++q) v = fma(R[q][c], -R[q][p], v);
-            R[p][c] = v / rk[p];
+            R[p][c] = v * inv[p];
         }
     }
     if (!pd) return false; // uniform: every thread computed the same values
@@ -235,7 +234,7 @@ __device__ __forceinline__ bool gs_factor_pass(double* __restrict__ J, int ld, i
                 double v = J[(k + p) + size_t(tid) * ld];
 #pragma unroll
                 for (int q = 0; q < p; ++q) v = fma(mu[q], -R[q][p], v);
-                mu[p] = v / rk[p];
+                mu[p] = v * inv[p];
                 cf[p] = -mu[p];
             }
         } else if (tid < k) { // row tid of the block columns
