@@ -66,7 +66,7 @@ def k6_algorithmic_flops(sz, iters):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the K6 kernel from the committed
 # `ncu --set full` capture (profiles/r01_gi_small_c2_ncu_raw.txt); only valid for that exact workload
-NCU_TRAFFIC = {("c2", 4096): 175850752 + 7036928}
+NCU_TRAFFIC = {("c2", 4096): 175565056 + 7223296}
 FP64_PEAK_TFLOPS = 37.0  # nominal B200 FP64 (vector == tensor); not in MEASURED_PEAKS.json
 
 
