@@ -228,3 +228,28 @@ def test_pycopra_autospan_and_system_checks_cpu():
     cost = copra.MixedCost(np.ones((1, 2)), np.ones((1, 1)), np.array([1.0, 2.0, 3.0]))
     cost.auto_span()
     assert cost._M.shape == (3, 8) and cost._N.shape == (3, 3) and cost._w.shape == (3,)
+
+
+def test_pycopra_dimension_errors_need_no_gpu():
+    """the reference's test_throw_handler scenario (binding/python/tests/pyTests.py:311-339): shape mismatches are
+    rejected on the host, before the engine is touched, as RuntimeError"""
+    from copra_b200 import pycopra as copra
+    T, mass, N = 0.005, 5.0, 300
+    A = np.array([[1.0, T], [0.0, 1.0]])
+    B = np.array([[0.5 * T * T / mass], [T / mass]])
+    ps = copra.PreviewSystem(A, B, np.zeros(2), np.array([0.0, -5.0]), N)
+    ctl = copra.LMPC(ps)
+    bad = [copra.TrajectoryConstraint(np.identity(5), np.ones(2)), copra.ControlConstraint(np.identity(5), np.ones(2)),
+           copra.MixedConstraint(np.identity(5), np.identity(5), np.ones(2)),
+           copra.TrajectoryBoundConstraint(np.ones(3), np.ones(3)), copra.ControlBoundConstraint(np.ones(3), np.ones(3)),
+           copra.TrajectoryConstraint(np.ones((2, 3)), np.ones(2))]
+    for c in bad:
+        with pytest.raises(RuntimeError):
+            ctl.add_constraint(c)
+    for c in (copra.TargetCost(np.identity(5), np.ones(2)), copra.ControlCost(np.ones((1, 2)), np.ones(1)),
+              copra.MixedCost(np.ones((1, 2)), np.ones((1, N)), np.ones(1))):
+        with pytest.raises(RuntimeError):
+            ctl.add_cost(c)
+    with pytest.raises(RuntimeError):
+        copra.TrajectoryBoundConstraint(np.ones(3), np.ones(2))
+    assert ctl._costs == [] and ctl._cstrs == []
