@@ -7,6 +7,7 @@
 #include "engine.cuh"
 #include "launch.h"
 #include "gi_solver.cuh"
+#include "gi_thin.cuh"
 
 #include <cfloat>
 #include <cmath>
@@ -56,6 +57,11 @@ struct copra_b200_handle {
     std::vector<int> lines_host;
     // state of the last build
     bool built = false;
+    bool factor_valid = false; // the thin solver's R^-1 of the last build is resident (re-solves skip the factorisation)
+    bool rows_filled = false;  // Aeq / Aineq of the last build are materialised (the structured solver never reads them)
+    bool use_thin = false;     // the last build is solved by the thin kernel (gi_thin.cuh)
+    GtBatch gt{};
+    GtPlan gtplan{};
     BuildParams bp{};
     Sizes sz;
     double vsmall = 0;
@@ -413,6 +419,98 @@ int run_gi(copra_b200_handle* h, GiBatch& G)
     return 0;
 }
 
+// Decide whether the build in h->bp goes to the thin solver (gi_thin.cuh): LMPC mode, more variables than the small
+// kernel takes, and every general row a step-size (block-Toeplitz) row whose tables fit shared memory.
+bool plan_thin(copra_b200_handle* h)
+{
+    const BuildParams& P = h->bp;
+    h->use_thin = false;
+    if (getenv("COPRA_B200_LEGACY_SOLVER")) return false;
+    if (P.initial_state) return false;
+    const int sms = h->sm_limit > 0 ? std::min(h->sm_limit, h->sms) : h->sms;
+    const GiPlan legacy = gi_plan(P.nvar, P.meq, P.mineq, P.batch, sms, h->smem_optin);
+    if (legacy.small) return false;
+    // a handful of instances: the cluster kernel spreads ONE instance over several SMs (latency); the thin kernel is the
+    // throughput design (one SM per instance) and wins as soon as the clusters would not cover the batch in one wave
+    if (legacy.cluster > 0 && P.batch * legacy.cluster * 2 <= sms && !getenv("COPRA_B200_THIN_SOLVER")) return false;
+    GtBatch& T = h->gt;
+    std::memset(&T, 0, sizeof T);
+    T.n = P.nvar; T.meq = P.meq; T.m = P.mineq; T.batch = P.batch;
+    T.structured = 1; T.nu = P.nu; T.N = P.N; T.nfam = P.nfam;
+    int tab = 0;
+    for (int k = 0; k < P.nfam; ++k) {
+        const CstrFam& F = P.fam[k];
+        if (F.dense || F.gather) return false;
+        GtFam& f = T.fam[k];
+        f.rows = F.rows; f.i0 = F.i0; f.i1 = F.i1; f.is_eq = F.is_eq; f.row_off = F.row_off;
+        f.tab = tab;
+        tab += F.rows * P.nu * (P.N + 1);
+    }
+    T.tab_doubles = tab;
+    h->gtplan = gt_plan(T.n, T.meq, T.m, tab, T.batch, sms, h->smem_optin);
+    if (!h->gtplan.ok) return false;
+    h->use_thin = true;
+    return true;
+}
+
+int run_gt(copra_b200_handle* h, double* x, int* status, int* iters, int* nact, int* iact)
+{
+    const BuildParams& P = h->bp;
+    GtBatch& T = h->gt;
+    const GtPlan& plan = h->gtplan;
+    const int sms = h->sm_limit > 0 ? std::min(h->sm_limit, h->sms) : h->sms;
+    const size_t n = P.nvar, count = P.sQ ? size_t(P.batch) : 1;
+    int rc;
+    double *Jt = nullptr, *JtT = nullptr, *wsp = nullptr;
+    int *pd = nullptr, *counter = nullptr;
+    if ((rc = ws(h, "gt_Jt", count * n * n, &Jt))) return rc;
+    if ((rc = ws(h, "gt_JtT", count * n * n, &JtT))) return rc;
+    if ((rc = ws(h, "gt_pd", count, &pd))) return rc;
+    if ((rc = ws(h, "gt_ws", size_t(plan.grid) * plan.ws_stride, &wsp))) return rc;
+    if ((rc = ws(h, "counter", 2, &counter))) return rc;
+    if (!h->factor_valid) {
+        cudaError_t e = gt_factor_launch(DArr{ P.Q, P.sQ }, P.nvar, int(count), Jt, JtT, pd, sms, h->stream);
+        if (e != cudaSuccess) return fail(h, COPRA_B200_E_CUDA, "gt_factor_launch: %s", cudaGetErrorString(e));
+        h->launches += 1; h->call_launches += 1;
+        h->factor_valid = true;
+    }
+    CU(cudaMemsetAsync(counter, 0, 2 * sizeof(int), h->stream));
+    for (int k = 0; k < P.nfam; ++k) { T.fam[k].EGx = P.fam[k].EGx; T.fam[k].sEGx = P.fam[k].sEGx; }
+    const long long nn = (long long)(n * n);
+    T.Jt = DArr{ Jt, P.sQ ? nn : 0 };
+    T.JtT = DArr{ JtT, P.sQ ? nn : 0 };
+    T.pd = pd; T.pd_stride = P.sQ ? 1 : 0;
+    T.c = DArr{ P.c, (long long)n };
+    T.Aeq = DArr{ nullptr, 0 }; T.Aineq = DArr{ nullptr, 0 };
+    T.beq = DArr{ P.meq ? P.beq : nullptr, P.meq };
+    T.bineq = DArr{ P.mineq ? P.bineq : nullptr, P.mineq };
+    T.lb = DArr{ P.lb, (long long)n };
+    T.ub = DArr{ P.ub, (long long)n };
+    T.x = x; T.status = status; T.iters = iters; T.nact = nact; T.iact = iact;
+    T.ws = wsp; T.ws_stride = plan.ws_stride;
+    T.counter = counter;
+    T.vsmall = h->vsmall;
+    T.max_iter = 50 * (P.meq + P.mineq + 2 * P.nvar) + 100;
+    cudaError_t e = gt_launch(T, plan, h->stream);
+    if (e != cudaSuccess) return fail(h, COPRA_B200_E_CUDA, "gt_launch: %s", cudaGetErrorString(e));
+    h->launches += 1; h->call_launches += 1;
+    return 0;
+}
+
+// materialise Aeq / Aineq of the last build if the build skipped them
+int ensure_rows(copra_b200_handle* h)
+{
+    if (h->rows_filled) return 0;
+    BuildParams& P = h->bp;
+    const size_t Bz = P.batch, nv = P.nvar;
+    int rc;
+    if ((rc = ws(h, "Aeq", Bz * P.meq * nv, &P.Aeq))) return rc;
+    if ((rc = ws(h, "Aineq", Bz * P.mineq * nv, &P.Aineq))) return rc;
+    LAUNCHED(k3_fill_rows_launch(P, h->stream));
+    h->rows_filled = true;
+    return 0;
+}
+
 int do_build(copra_b200_handle* h, const copra_b200_problem* p)
 {
     Plan pl;
@@ -434,6 +532,15 @@ int do_build(copra_b200_handle* h, const copra_b200_problem* p)
     P.qdiag = (p->flags & COPRA_B200_FLAG_NO_REG) ? 0.0 : 1e-6;
     P.ncost = int(pl.costs.size());
     P.nfam = int(pl.fams.size());
+    // The Hessian is a function of A, B and every cost's M, N, w only (p, x0 and the constraints enter c / b): when all of
+    // those are shared by the batch it is assembled and factored ONCE (src/costFunctions.cpp:74-75,103-104,150-152,206-208).
+    bool q_shared = !p->initial_state && p->A.stride == 0 && p->B.stride == 0 && B > 1;
+    for (int i = 0; i < p->ncost && q_shared; ++i) {
+        const copra_b200_cost& c = p->costs[i];
+        if (c.full_size || (c.M.ptr && c.M.stride != 0) || (c.N.ptr && c.N.stride != 0) || c.w.stride != 0) q_shared = false;
+    }
+    if (getenv("COPRA_B200_NO_SHARED_HESSIAN")) q_shared = false;
+    P.sQ = q_shared ? 0 : (long long)pl.sz.nvar * pl.sz.nvar;
 
     // selector matrices + line indices for TrajectoryBound families (tiny, shared by all instances)
     std::vector<double> sel;
@@ -533,11 +640,14 @@ int do_build(copra_b200_handle* h, const copra_b200_problem* p)
     if ((rc = ws(h, "Phi", Bz * X * nx, &P.Phi))) return rc;
     if ((rc = ws(h, "Gs", Bz * size_t(N) * nx * nu, &P.Gs))) return rc;
     if ((rc = ws(h, "xi", Bz * X, &P.xi))) return rc;
-    if ((rc = ws(h, "Q", Bz * nv * nv, &P.Q))) return rc;
+    if ((rc = ws(h, "Q", (P.sQ ? Bz : size_t(1)) * nv * nv, &P.Q))) return rc;
     if ((rc = ws(h, "c", Bz * nv, &P.c))) return rc;
-    if ((rc = ws(h, "Aeq", Bz * meq * nv, &P.Aeq))) return rc;
+    plan_thin(h);
+    P.skip_rows = h->use_thin ? 1 : 0; // the structured solver evaluates the rows from the E A^k B tables
+    P.Aeq = P.Aineq = nullptr;
+    if (!P.skip_rows && (rc = ws(h, "Aeq", Bz * meq * nv, &P.Aeq))) return rc;
     if ((rc = ws(h, "beq", Bz * meq, &P.beq))) return rc;
-    if ((rc = ws(h, "Aineq", Bz * m * nv, &P.Aineq))) return rc;
+    if (!P.skip_rows && (rc = ws(h, "Aineq", Bz * m * nv, &P.Aineq))) return rc;
     if ((rc = ws(h, "bineq", Bz * m, &P.bineq))) return rc;
     if ((rc = ws(h, "lb", Bz * nv, &P.lb))) return rc;
     if ((rc = ws(h, "ub", Bz * nv, &P.ub))) return rc;
@@ -591,6 +701,8 @@ int do_build(copra_b200_handle* h, const copra_b200_problem* p)
     if ((rc = record(h, 3))) return rc;
     h->sz = pl.sz;
     h->built = true;
+    h->factor_valid = false;
+    h->rows_filled = !P.skip_rows;
     return 0;
 }
 
@@ -621,7 +733,7 @@ int do_solve(copra_b200_handle* h, const copra_b200_results* r)
     }
     GiBatch G{};
     G.n = P.nvar; G.meq = P.meq; G.m = P.mineq; G.batch = P.batch;
-    G.Q = DArr{ P.Q, (long long)(nv * nv) };
+    G.Q = DArr{ P.Q, P.sQ };
     G.c = DArr{ P.c, (long long)nv };
     G.Aeq = DArr{ P.meq ? P.Aeq : nullptr, (long long)(size_t(P.meq) * nv) };
     G.beq = DArr{ P.meq ? P.beq : nullptr, P.meq };
@@ -630,7 +742,14 @@ int do_solve(copra_b200_handle* h, const copra_b200_results* r)
     G.lb = DArr{ P.lb, (long long)nv };
     G.ub = DArr{ P.ub, (long long)nv };
     G.x = x; G.status = status; G.iters = iters; G.nact = nact; G.iact = iact;
-    if ((rc = run_gi(h, G))) return rc;
+    if (h->use_thin) {
+        if ((rc = run_gt(h, x, status, iters, nact, iact))) return rc;
+    } else {
+        if ((rc = ensure_rows(h))) return rc;
+        G.Aeq.p = P.meq ? h->bp.Aeq : nullptr;
+        G.Aineq.p = P.mineq ? h->bp.Aineq : nullptr;
+        if ((rc = run_gi(h, G))) return rc;
+    }
     if ((rc = record(h, 4))) return rc;
     const bool want_ct = !r || r->control || r->trajectory;
     if (want_ct) LAUNCHED(k7_results_launch(P, x, control, traj, h->stream));
@@ -926,10 +1045,27 @@ int copra_b200_lmpc_download(copra_b200_handle* h, int what, double* out, int me
 {
     if (!h || !out) return COPRA_B200_E_ARG;
     if (!h->built) return fail(h, COPRA_B200_E_STATE, "download before build");
+    CU(cudaSetDevice(h->device));
+    h->call_launches = 0;
+    if (what == COPRA_B200_GET_AEQ || what == COPRA_B200_GET_AINEQ) {
+        int rc = ensure_rows(h);
+        if (rc) return rc;
+    }
     const BuildParams& P = h->bp;
     const size_t B = P.batch, nv = P.nvar;
     const double* src = nullptr;
     size_t count = 0;
+    if (what == COPRA_B200_GET_Q && P.sQ == 0) { // batch-invariant Hessian: one resident copy, replicated for the caller
+        const size_t bytes = nv * nv * sizeof(double);
+        if (memory == COPRA_B200_DEVICE) {
+            for (size_t b = 0; b < B; ++b) CU(cudaMemcpyAsync(out + b * nv * nv, P.Q, bytes, cudaMemcpyDeviceToDevice, h->stream));
+        } else {
+            CU(cudaMemcpyAsync(out, P.Q, bytes, cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            for (size_t b = 1; b < B; ++b) std::memcpy(out + b * nv * nv, out, bytes);
+        }
+        return 0;
+    }
     switch (what) {
     case COPRA_B200_GET_PHI: src = P.Phi; count = B * P.X * P.nx; break;
     case COPRA_B200_GET_XI: src = P.xi; count = B * P.X; break;

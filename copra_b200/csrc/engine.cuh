@@ -68,6 +68,7 @@ struct BuildParams {
     DArr R, r, x0lb, x0ub;        // initial-state mode (p may be null)
     DArr cb_lower, cb_upper;      // ControlBoundConstraint (p null = none)
     int cb_full;                  // 1: lower/upper hold nU entries (full-size entry)
+    int skip_rows;                // 1: Aeq / Aineq are not materialised by the build (structured solver; filled on demand)
     double* PsiFull;              // X x nU per instance, only materialised when a full-size entry needs it
     // K1 outputs (workspace, per instance)
     double* Phi;   // X x nx
@@ -75,6 +76,7 @@ struct BuildParams {
     double* xi;    // X
     // assembled QP (per instance)
     double* Q;     // nvar x nvar
+    long long sQ;  // doubles between the Hessians of consecutive instances; 0 = batch-invariant Hessian (one copy)
     double* c;     // nvar
     double* Aeq;   // meq x nvar
     double* beq;

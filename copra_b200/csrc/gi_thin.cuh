@@ -1,0 +1,645 @@
+// gi_thin.cuh -- K5+K6 for n > 64: a THROUGHPUT-oriented Goldfarb-Idnani solver, one CTA per instance on one SM.
+//
+// Same problem, index space, selection / step / drop rules and fail codes as gi_solver.cuh (QuadProgDenseSolver::SI_solve,
+// reference src/QuadProgSolver.cpp:54-72, and qpgen2 behind it); what changes is the representation of the
+// factorisation, chosen so that the per-instance MUTABLE state is small and the big matrix is read-only:
+//
+//   qpgen2 / gi_solver.cuh : J = R^-1 Qfull  (n x n, rewritten by every add / drop)           -> 8 n^2 bytes of state
+//   here                   : Jt = R^-1       (n x n upper triangular, NEVER modified; one copy per distinct Hessian --
+//                                             a single one for the whole batch when the Hessian is batch-invariant)
+//                            Q1 = first nact columns of Qfull (n x nact, orthonormal)          -> 8 n nact bytes
+//                            S  = (Q1' Jt' N)^-1 (nact x nact)                                 -> 8 nact^2 bytes
+//   d  = Jt' a (triangular mat-vec),  d1 = Q1' d,  zt = d - Q1 d1 (= Q2 Q2' d),  z = Jt zt,  r = S d1
+//   ADD  : Q1 gains the column zt/|zt|, S the column [-r/|zt| ; 1/|zt|]   (no rotation of anything)
+//   DROP : one reflection of Q1 and S whose last column is the dropped row of S (as in gi_solver.cuh)
+// In exact arithmetic d1, |d2| = |zt|, z, r and therefore every iterate are those of qpgen2.
+//
+// Because Jt is read-only it is factored ONCE per distinct Hessian by gt_factor_kernel (blocked DMMA Cholesky + inverse,
+// gi_factor.cuh) instead of once per solve, it is shared by every CTA through L2, and a receding-horizon re-solve reuses it.
+//
+// General rows [Aeq; Aineq] of a step-size LMPC are block-Toeplitz (row of step i, block column j = E A^(i-1-j) B, G at
+// j == i; reference src/constraints.cpp:77,142,209-219): their products with x are evaluated straight from the per-family
+// r x nu x (N+1) tables in shared memory (a causal convolution), so the m x n matrix is never read by the solver.  A dense
+// mode (rows streamed from global memory) serves full-size entries.
+#pragma once
+#include "common.cuh"
+#include "engine.cuh"
+#include "gi_solver.cuh"
+
+namespace cb {
+
+struct GtFam {
+    int rows, i0, i1, is_eq, row_off; // row_off: first row inside Aeq (is_eq) or Aineq
+    int tab;                          // offset of this family's table in the shared-memory table area (doubles)
+    const double* EGx;                // r x nu x (N+1) per instance: block kk = E A^(kk-1) B (kk >= 1), G | 0 (kk == 0)
+    long long sEGx;
+};
+
+struct GtBatch {
+    int n, meq, m, batch;
+    int structured, nu, N, nfam, tab_doubles;
+    GtFam fam[kMaxFam];
+    DArr Jt, JtT;       // R^-1 column-major (entries i <= j of column j) and its transpose (entries j >= i of column i)
+    const int* pd;      // 1 = Hessian positive definite, per distinct Hessian
+    int pd_stride;      // 0 (shared) or 1
+    DArr c, Aeq, beq, Aineq, bineq, lb, ub;
+    double* x;
+    int *status, *iters, *nact, *iact;
+    double* ws;         // per CTA: Q1 (n x n, ld n) then S (n x n, ld n)
+    long long ws_stride;
+    int* counter;
+    double vsmall;
+    int max_iter;
+};
+
+struct GtLayout {
+    size_t oTab, oX, oD, oZt, oZ, oAv, oR, oU, oD1, oW, oV, oLb, oUb, oSl, oB, oNorm, oRed, oPart; // doubles
+    size_t oIact, oRowmap, oRedI, oActive, oSgn, bytes;                                             // bytes
+};
+
+__host__ __device__ inline GtLayout gt_layout(int n, int meq, int m, int tab_doubles, int threads)
+{
+    GtLayout L;
+    const int mg = meq + m;
+    size_t o = 0;
+    L.oTab = o; o += (size_t(tab_doubles) + 1) & ~size_t(1);
+    L.oX = o; o += n;
+    L.oD = o; o += n;
+    L.oZt = o; o += n;
+    L.oZ = o; o += n;
+    L.oAv = o; o += n;
+    L.oR = o; o += n;
+    L.oU = o; o += n + 1;
+    L.oD1 = o; o += n;
+    L.oW = o; o += n;
+    L.oV = o; o += n;
+    L.oLb = o; o += n;
+    L.oUb = o; o += n;
+    L.oSl = o; o += mg;
+    L.oB = o; o += mg;
+    L.oNorm = o; o += mg;
+    L.oRed = o; o += 4 * kMaxWarps;
+    L.oPart = o; o += 2 * size_t(threads) + 64;
+    size_t b = o * sizeof(double);
+    L.oIact = b; b += sizeof(int) * size_t(n);
+    L.oRowmap = b; b += sizeof(int) * size_t(n);
+    L.oRedI = b; b += sizeof(int) * kMaxWarps;
+    L.oActive = b; b += size_t(mg + 2 * n);
+    L.oSgn = b; b += size_t(meq > 0 ? meq : 1);
+    L.bytes = (b + 15) & ~size_t(15);
+    return L;
+}
+
+struct GtWork {
+    double *tab, *x, *d, *zt, *z, *av, *r, *u, *d1, *w, *v, *lb, *ub, *sl, *bv, *norm, *red, *part;
+    int *iact, *rowmap, *redi;
+    unsigned char* active;
+    signed char* sgn;
+    double *Q1, *S;
+};
+
+__device__ inline GtWork gt_carve(const GtLayout& L, unsigned char* smem, double* ws, int n)
+{
+    GtWork W;
+    double* base = reinterpret_cast<double*>(smem);
+    W.tab = base + L.oTab; W.x = base + L.oX; W.d = base + L.oD; W.zt = base + L.oZt; W.z = base + L.oZ;
+    W.av = base + L.oAv; W.r = base + L.oR; W.u = base + L.oU; W.d1 = base + L.oD1; W.w = base + L.oW; W.v = base + L.oV;
+    W.lb = base + L.oLb; W.ub = base + L.oUb; W.sl = base + L.oSl; W.bv = base + L.oB; W.norm = base + L.oNorm;
+    W.red = base + L.oRed; W.part = base + L.oPart;
+    W.iact = reinterpret_cast<int*>(smem + L.oIact);
+    W.rowmap = reinterpret_cast<int*>(smem + L.oRowmap);
+    W.redi = reinterpret_cast<int*>(smem + L.oRedI);
+    W.active = smem + L.oActive;
+    W.sgn = reinterpret_cast<signed char*>(smem + L.oSgn);
+    W.Q1 = ws;
+    W.S = ws + size_t(n) * n;
+    return W;
+}
+
+// ---- triangular mat-vecs against the read-only factor: one warp per output, four outputs and two strides in flight ----
+// out[c] = sum_{k < len(c)} M[base(c) + k] * vec[voff(c) + k],  c in [0, nout)
+template <class FB, class FL, class FO>
+__device__ __forceinline__ void gt_seg_dots(const double* __restrict__ M, int nout, FB base, FL len, FO voff,
+    const double* __restrict__ vec, double* __restrict__ out)
+{
+    const int lane = lane_id(), wp = warp_id(), nw = blockDim.x >> 5;
+    for (int c = 4 * wp; c < nout; c += 4 * nw) {
+        const double* m[4];
+        const double* v[4];
+        int ln[4];
+        int lmax = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int cc = min(c + u, nout - 1);
+            m[u] = M + base(cc);
+            v[u] = vec + voff(cc);
+            ln[u] = (c + u < nout) ? len(cc) : 0;
+            lmax = max(lmax, ln[u]);
+        }
+        double s[4] = { 0.0, 0.0, 0.0, 0.0 };
+        double t[4] = { 0.0, 0.0, 0.0, 0.0 };
+        for (int k = lane; k < lmax; k += 64) {
+            double a0[4], a1[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                a0[u] = (k < ln[u]) ? __ldg(m[u] + k) : 0.0;
+                a1[u] = (k + 32 < ln[u]) ? __ldg(m[u] + k + 32) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (k < ln[u]) s[u] = fma(a0[u], v[u][k], s[u]);
+                if (k + 32 < ln[u]) t[u] = fma(a1[u], v[u][k + 32], t[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            double q = s[u] + t[u];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+            if (lane == 0 && c + u < nout) out[c + u] = q;
+        }
+    }
+}
+
+// d[j] = sum_{i <= j, i < supp} Jt[i, j] a[i]
+__device__ __forceinline__ void gt_jt_dots(const double* __restrict__ Jt, int n, int supp, const double* __restrict__ a,
+    double* __restrict__ d)
+{
+    gt_seg_dots(Jt, n, [&](int j) { return size_t(j) * n; }, [&](int j) { return min(j + 1, supp); }, [](int) { return 0; }, a, d);
+}
+// z[i] = sum_{j >= i} Jt[i, j] v[j]   (JtT[j + i n] = Jt[i, j])
+__device__ __forceinline__ void gt_j_dots(const double* __restrict__ JtT, int n, const double* __restrict__ v, double* __restrict__ z)
+{
+    gt_seg_dots(JtT, n, [&](int i) { return size_t(i) * n + i; }, [&](int i) { return n - i; }, [](int i) { return i; }, v, z);
+}
+
+// out[r] = sum_{c in [c0,c1)} M[rowof(r) + c*ld] * vec[c], r in [0, rows): lanes along rows, the column range split over
+// G = T / round32(rows) thread groups when the CTA has more threads than rows; four independent loads in flight per thread.
+// Contains one __syncthreads when the split is active; the caller syncs before reading `out`.
+template <class FR>
+__device__ __forceinline__ void gt_row_dots(const double* __restrict__ M, size_t ld, int rows, int c0, int c1, FR rowof,
+    const double* __restrict__ vec, double* __restrict__ out, double* __restrict__ part)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int rp = max(32, round32(rows));
+    const int G = max(1, T / rp);
+    if (G <= 1) {
+        for (int r = tid; r < rows; r += T) {
+            const double* mr = M + rowof(r);
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int c = c0;
+            for (; c + 3 < c1; c += 4) {
+                const double m0 = mr[size_t(c) * ld], m1 = mr[size_t(c + 1) * ld], m2 = mr[size_t(c + 2) * ld], m3 = mr[size_t(c + 3) * ld];
+                s0 = fma(m0, vec[c], s0);
+                s1 = fma(m1, vec[c + 1], s1);
+                s2 = fma(m2, vec[c + 2], s2);
+                s3 = fma(m3, vec[c + 3], s3);
+            }
+            for (; c < c1; ++c) s0 = fma(mr[size_t(c) * ld], vec[c], s0);
+            out[r] = (s0 + s1) + (s2 + s3);
+        }
+        return;
+    }
+    const int g = tid / rp, r = tid - g * rp;
+    if (g < G && r < rows) {
+        const double* mr = M + rowof(r);
+        double s0 = 0.0, s1 = 0.0;
+        int c = c0 + g;
+        for (; c + G < c1; c += 2 * G) {
+            const double m0 = mr[size_t(c) * ld], m1 = mr[size_t(c + G) * ld];
+            s0 = fma(m0, vec[c], s0);
+            s1 = fma(m1, vec[c + G], s1);
+        }
+        if (c < c1) s0 = fma(mr[size_t(c) * ld], vec[c], s0);
+        part[g * rp + r] = s0 + s1;
+    }
+    __syncthreads();
+    if (tid < rows) {
+        double s = part[tid];
+        for (int k = 1; k < G; ++k) s += part[k * rp + tid];
+        out[tid] = s;
+    }
+}
+
+// ---- structured general rows -------------------------------------------------------------------------------------------
+// sl[row] = sum_{j <= min(i, N-1)} sum_bb T[l + r (bb + nu (i - j))] x[j nu + bb]   for every row (family, step i, line l).
+// One warp per (4 steps x 4 lines) tile: the lanes split the kk = i - j range, keep 16 accumulators and meet in a
+// 16-shuffle transpose-reduction; fixed summation order (deterministic).
+__device__ __forceinline__ void gt_products(const GtBatch& B, const GtWork& W)
+{
+    const int nu = B.nu, N = B.N;
+    const int lane = lane_id(), wp = warp_id(), nw = blockDim.x >> 5;
+    int task0 = 0;
+    for (int fi = 0; fi < B.nfam; ++fi) {
+        const GtFam& F = B.fam[fi];
+        const int r = F.rows, ns = F.i1 - F.i0;
+        const int nsb = (ns + 3) >> 2, nrg = (r + 3) >> 2, ntask = nsb * nrg;
+        const double* tab = W.tab + F.tab;
+        double* out = W.sl + (F.is_eq ? 0 : B.meq) + F.row_off;
+        int t = (wp - task0 % nw + nw) % nw;
+        for (; t < ntask; t += nw) {
+            // long tiles (late steps) first within a warp's list does not matter: cyclic deal balances well enough
+            const int sb = nsb - 1 - t / nrg, rg = t % nrg;
+            const int ib = F.i0 + 4 * sb, l0 = 4 * rg;
+            const int kk_lo = max(0, ib - (N - 1)), kk_hi = min(ib + 3, F.i1 - 1);
+            double acc[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+            for (int kk = kk_lo + lane; kk <= kk_hi; kk += 32) {
+                for (int bb = 0; bb < nu; ++bb) {
+                    const double* tp = tab + l0 + r * (bb + nu * kk);
+                    double tv[4], xv[4];
+#pragma unroll
+                    for (int ll = 0; ll < 4; ++ll) tv[ll] = (l0 + ll < r) ? tp[ll] : 0.0;
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        const int j = ib + s - kk;
+                        xv[s] = (j >= 0 && j < N && ib + s < F.i1) ? W.x[j * nu + bb] : 0.0;
+                    }
+#pragma unroll
+                    for (int s = 0; s < 4; ++s)
+#pragma unroll
+                        for (int ll = 0; ll < 4; ++ll) acc[4 * s + ll] = fma(tv[ll], xv[s], acc[4 * s + ll]);
+                }
+            }
+            // transpose-reduce: afterwards lane 2e (e = 0..15) holds the total of acc[e]
+#pragma unroll
+            for (int o = 16, cnt = 16; cnt > 1; o >>= 1, cnt >>= 1) {
+                const int half = cnt >> 1;
+                const bool up = (lane & o) != 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (k < half) {
+                        const double send = up ? acc[k] : acc[k + half];
+                        const double recv = __shfl_xor_sync(0xffffffffu, send, o);
+                        acc[k] = (up ? acc[k + half] : acc[k]) + recv;
+                    }
+                }
+            }
+            acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+            if ((lane & 1) == 0) {
+                const int e = lane >> 1, s = e >> 2, ll = e & 3;
+                if (ib + s < F.i1 && l0 + ll < r) out[(ib + s - F.i0) * r + l0 + ll] = acc[0];
+            }
+        }
+        task0 += ntask;
+    }
+}
+
+// locate general row `g` (0-based in [eq | ineq]) in the family list: family, step and line
+__device__ __forceinline__ void gt_locate(const GtBatch& B, int g, int& fi, int& step, int& line)
+{
+    const bool iseq = g < B.meq;
+    const int lrow = iseq ? g : g - B.meq;
+    fi = 0;
+    for (int k = 0; k < B.nfam; ++k) {
+        const GtFam& F = B.fam[k];
+        if ((F.is_eq != 0) == iseq && lrow >= F.row_off && lrow < F.row_off + F.rows * (F.i1 - F.i0)) { fi = k; break; }
+    }
+    const GtFam& F = B.fam[fi];
+    step = F.i0 + (lrow - F.row_off) / F.rows;
+    line = (lrow - F.row_off) % F.rows;
+}
+
+// entry k of general row (family F, step, line)
+__device__ __forceinline__ double gt_row_entry(const GtBatch& B, const double* tab, const GtFam& F, int step, int line, int k)
+{
+    const int j = k / B.nu, bb = k - j * B.nu, kk = step - j;
+    return (kk >= 0) ? tab[F.tab + line + F.rows * (bb + B.nu * kk)] : 0.0;
+}
+
+// ---- the solver ----------------------------------------------------------------------------------------------------------
+__device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double vsmall, int max_iter)
+{
+    const int n = B.n, meq = B.meq, m = B.m, mg = meq + m, q = mg + 2 * n;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const size_t ldn = size_t(n);
+    const double* __restrict__ Jt = B.Jt.at(b);
+    const double* __restrict__ JtT = B.JtT.at(b);
+    double* __restrict__ Q1 = W.Q1;
+    double* __restrict__ S = W.S;
+    double* scal = W.red + 2 * kMaxWarps;
+    const double* gc = B.c.at(b);
+    const double* gAeq = B.Aeq.p ? B.Aeq.at(b) : nullptr;
+    const double* gAin = B.Aineq.p ? B.Aineq.at(b) : nullptr;
+
+    // ---- 0. load ----------------------------------------------------------------------------------------------------------
+    if (B.structured) {
+        for (int fi = 0; fi < B.nfam; ++fi) {
+            const GtFam& F = B.fam[fi];
+            const double* src = F.EGx + (long long)b * F.sEGx;
+            const int cnt = F.rows * B.nu * (B.N + 1);
+            for (int t = tid; t < cnt; t += T) W.tab[F.tab + t] = src[t];
+        }
+    }
+    {
+        const double* glb = B.lb.at(b);
+        const double* gub = B.ub.at(b);
+        for (int i = tid; i < n; i += T) {
+            W.av[i] = -gc[i];
+            W.lb[i] = glb[i];
+            W.ub[i] = gub[i];
+            W.u[i] = 0.0;
+            W.iact[i] = 0;
+            W.rowmap[i] = i;
+        }
+        if (tid == 0) W.u[n] = 0.0;
+        const double* gbe = meq ? B.beq.at(b) : nullptr;
+        const double* gbi = m ? B.bineq.at(b) : nullptr;
+        for (int i = tid; i < mg; i += T) W.bv[i] = (i < meq) ? gbe[i] : gbi[i - meq];
+        for (int i = tid; i < q; i += T) W.active[i] = 0;
+        for (int i = tid; i < meq; i += T) W.sgn[i] = 1;
+    }
+    __syncthreads();
+
+    int fail = 0, nact = 0, iter0 = 0, iter1 = 0;
+    if (B.pd[(long long)b * B.pd_stride] == 0) fail = 2;
+
+    if (fail == 0) {
+        // ---- unconstrained minimiser x = Jt Jt' (-c) -------------------------------------------------------------------------
+        gt_jt_dots(Jt, n, n, W.av, W.d);
+        // ---- norms of the general rows (the reference's summation order: columns ascending) ---------------------------------
+        for (int i = tid; i < mg; i += T) {
+            double s = 0.0;
+            if (B.structured) {
+                int fi, step, line;
+                gt_locate(B, i, fi, step, line);
+                const GtFam& F = B.fam[fi];
+                const int jmax = min(step, B.N - 1);
+                for (int j = 0; j <= jmax; ++j)
+                    for (int bb = 0; bb < B.nu; ++bb) {
+                        const double v = W.tab[F.tab + line + F.rows * (bb + B.nu * (step - j))];
+                        s += v * v;
+                    }
+            } else if (i < meq) {
+                for (int k = 0; k < n; ++k) { const double v = gAeq[i + size_t(k) * meq]; s += v * v; }
+            } else {
+                for (int k = 0; k < n; ++k) { const double v = gAin[(i - meq) + size_t(k) * m]; s += v * v; }
+            }
+            W.norm[i] = sqrt(s);
+        }
+        __syncthreads();
+        gt_j_dots(JtT, n, W.d, W.x);
+        __syncthreads();
+
+        // ---- dual active-set iterations ----------------------------------------------------------------------------------------
+        for (;;) {
+            ++iter0;
+            if (iter0 > max_iter) { fail = 3; break; }
+            // all slacks; most violated normalised constraint, lowest index on ties
+            if (mg > 0) {
+                if (B.structured) gt_products(B, W);
+                else {
+                    if (meq) gt_row_dots(gAeq, size_t(meq), meq, 0, n, [](int r_) { return size_t(r_); }, W.x, W.sl, W.part);
+                    if (meq && m) __syncthreads();
+                    if (m) gt_row_dots(gAin, size_t(m), m, 0, n, [](int r_) { return size_t(r_); }, W.x, W.sl + meq, W.part);
+                }
+            }
+            __syncthreads();
+            MinIdx best; best.v = 0.0; best.i = -1;
+            double best_s = 0.0;
+            for (int i = tid; i < q; i += T) {
+                double s;
+                if (i < meq) s = double(W.sgn[i]) * (W.sl[i] - W.bv[i]);
+                else if (i < mg) s = W.bv[i] - W.sl[i];
+                else if (i < mg + n) s = W.ub[i - mg] - W.x[i - mg];
+                else s = W.x[i - mg - n] - W.lb[i - mg - n];
+                if (fabs(s) < vsmall) s = 0.0;
+                if (i < meq) {
+                    if (s > 0.0) W.sgn[i] = -W.sgn[i];
+                    s = -fabs(s);
+                }
+                if (W.active[i]) s = 0.0;
+                if (s < 0.0) {
+                    const double nrm = (i < mg) ? W.norm[i] : 1.0;
+                    MinIdx c; c.v = s / nrm; c.i = i;
+                    const MinIdx nb = better(best, c);
+                    if (nb.i != best.i) best_s = s;
+                    best = nb;
+                }
+            }
+            const MinIdx sel = block_argmin(best, W.red, W.redi);
+            if (sel.i < 0) break; // optimal
+            const int nvl = sel.i;
+            if (best.i == nvl) scal[0] = best_s;
+            __syncthreads();
+            double s_nvl = scal[0];
+
+            // the signed normal a_nvl (quadprog orientation a'x >= b) and d = Jt' a: they do not change at label 55
+            int bj = -1, supp = n;
+            double bsign = 0.0;
+            if (nvl < mg) {
+                const double sg = (nvl < meq) ? double(W.sgn[nvl]) : -1.0;
+                if (B.structured) {
+                    int fi, step, line;
+                    gt_locate(B, nvl, fi, step, line);
+                    const GtFam& F = B.fam[fi];
+                    supp = min(step + 1, B.N) * B.nu;
+                    for (int k = tid; k < n; k += T) W.av[k] = (k < supp) ? sg * gt_row_entry(B, W.tab, F, step, line, k) : 0.0;
+                } else if (nvl < meq) {
+                    for (int k = tid; k < n; k += T) W.av[k] = sg * gAeq[nvl + size_t(k) * meq];
+                } else {
+                    for (int k = tid; k < n; k += T) W.av[k] = sg * gAin[(nvl - meq) + size_t(k) * m];
+                }
+                __syncthreads();
+                gt_jt_dots(Jt, n, supp, W.av, W.d);
+            } else {
+                const int j = nvl - mg;
+                if (j < n) { bj = j; bsign = -1.0; }
+                else { bj = j - n; bsign = 1.0; }
+                // d[j] = bsign * Jt[bj, j] (j >= bj): a contiguous run of the transposed factor
+                for (int k = tid; k < n; k += T) W.d[k] = (k >= bj) ? bsign * __ldg(JtT + size_t(bj) * n + k) : 0.0;
+            }
+            __syncthreads();
+            double dnorm2 = 0.0;
+            for (int k = tid; k < n; k += T) dnorm2 += W.d[k] * W.d[k];
+            dnorm2 = block_sum(dnorm2, W.red);
+
+            for (;;) { // label 55
+                // d1 = Q1' d ; zt = d - Q1 d1 (second pass when most of d cancelled: "twice is enough")
+                double dd = dnorm2;
+                if (nact > 0) {
+                    col_dots(Q1, int(ldn), n, 0, nact, W.d, W.d1);
+                    __syncthreads();
+                    gt_row_dots(Q1, ldn, n, 0, nact, [](int r_) { return size_t(r_); }, W.d1, W.w, W.part);
+                    __syncthreads();
+                    double acc = 0.0;
+                    for (int k = tid; k < n; k += T) { const double v = W.d[k] - W.w[k]; W.zt[k] = v; acc += v * v; }
+                    dd = block_sum(acc, W.red);
+                    if (dd < 0.25 * dnorm2) {
+                        col_dots(Q1, int(ldn), n, 0, nact, W.zt, W.v);
+                        __syncthreads();
+                        gt_row_dots(Q1, ldn, n, 0, nact, [](int r_) { return size_t(r_); }, W.v, W.w, W.part);
+                        __syncthreads();
+                        acc = 0.0;
+                        for (int k = tid; k < n; k += T) { const double v = W.zt[k] - W.w[k]; W.zt[k] = v; acc += v * v; }
+                        for (int k = tid; k < nact; k += T) W.d1[k] += W.v[k];
+                        dd = block_sum(acc, W.red);
+                    }
+                } else {
+                    for (int k = tid; k < n; k += T) W.zt[k] = W.d[k];
+                    __syncthreads();
+                }
+                // z = Jt zt ; r = S d1
+                gt_j_dots(JtT, n, W.zt, W.z);
+                if (nact > 0) gt_row_dots(S, ldn, nact, 0, nact, [&](int r_) { return size_t(W.rowmap[r_]); }, W.d1, W.r, W.part);
+                __syncthreads();
+                MinIdx tc; tc.v = 0.0; tc.i = -1;
+                for (int i = tid; i < nact; i += T) {
+                    if (W.iact[i] - 1 >= meq && W.r[i] > 0.0) {
+                        MinIdx c; c.v = W.u[i] / W.r[i]; c.i = i;
+                        tc = better(tc, c);
+                    }
+                }
+                const MinIdx t1m = block_argmin(tc, W.red, W.redi);
+                const bool t1inf = t1m.i < 0;
+                const double t1 = t1m.v;
+                const int it1 = t1m.i;
+                double zz = 0.0, za = 0.0;
+                for (int j = tid; j < n; j += T) {
+                    const double zj = W.z[j];
+                    zz += zj * zj;
+                    if (bj < 0) za += zj * W.av[j];
+                }
+                block_sum2(zz, za, W.red);
+                if (bj >= 0) za = bsign * W.z[bj];
+
+                bool do_drop = false;
+                if (fabs(zz) <= vsmall) {
+                    if (t1inf) { fail = 1; break; }
+                    for (int i = tid; i < nact; i += T) W.u[i] -= t1 * W.r[i];
+                    if (tid == 0) W.u[nact] += t1;
+                    do_drop = true;
+                } else {
+                    double tt = -s_nvl / za;
+                    bool t2min = true;
+                    if (!t1inf && t1 < tt) { tt = t1; t2min = false; }
+                    for (int j = tid; j < n; j += T) W.x[j] += tt * W.z[j];
+                    for (int i = tid; i < nact; i += T) W.u[i] -= tt * W.r[i];
+                    if (tid == 0) W.u[nact] += tt;
+                    if (t2min) {
+                        // ---- add constraint nvl: Q1 gains zt / delta, S the column [-r/delta ; 1/delta] ----------------------
+                        const double delta = sqrt(dd), inv = 1.0 / delta;
+                        double* qc = Q1 + size_t(nact) * ldn;
+                        for (int j = tid; j < n; j += T) qc[j] = W.zt[j] * inv;
+                        const int newrow = W.rowmap[nact];
+                        for (int i = tid; i < nact; i += T) {
+                            S[W.rowmap[i] + size_t(nact) * ldn] = -W.r[i] * inv;
+                            S[newrow + size_t(i) * ldn] = 0.0;
+                        }
+                        if (tid == 0) {
+                            S[newrow + size_t(nact) * ldn] = inv;
+                            W.iact[nact] = nvl + 1;
+                            W.active[nvl] = 1;
+                        }
+                        ++nact;
+                        __syncthreads();
+                        break; // next outer iteration
+                    } else {
+                        // partial step: refresh s_nvl at the new x (with the equality sign rule)
+                        __syncthreads();
+                        double s;
+                        if (bj >= 0) {
+                            s = (bsign < 0.0) ? W.ub[bj] - W.x[bj] : W.x[bj] - W.lb[bj];
+                        } else {
+                            double acc = 0.0; // av holds the signed normal, so a'x = av . x
+                            for (int k = tid; k < n; k += T) acc += W.av[k] * W.x[k];
+                            acc = block_sum(acc, W.red);
+                            if (nvl < meq) s = acc - double(W.sgn[nvl]) * W.bv[nvl];
+                            else s = acc + W.bv[nvl];
+                        }
+                        if (nvl < meq) {
+                            // the sign flip of an equality changes the orientation of a_nvl, hence of d: redo from the top
+                            __syncthreads();
+                            if (s > 0.0) {
+                                if (tid == 0) W.sgn[nvl] = -W.sgn[nvl];
+                                for (int k = tid; k < n; k += T) { W.av[k] = -W.av[k]; W.d[k] = -W.d[k]; }
+                            }
+                            s = -fabs(s);
+                        }
+                        s_nvl = s;
+                        do_drop = true;
+                    }
+                }
+                if (do_drop) {
+                    // ---- drop the it1-th active constraint: reflection with last column ~ row p of S ---------------------------
+                    __syncthreads();
+                    const int p = it1;
+                    const int dropped = (tid == 0) ? W.iact[p] - 1 : 0;
+                    const int prow = W.rowmap[p];
+                    if (nact > 1) {
+                        double vv = 0.0;
+                        for (int k = tid; k < nact; k += T) { const double t_ = S[prow + size_t(k) * ldn]; W.v[k] = t_; vv += t_ * t_; }
+                        vv = block_sum(vv, W.red);
+                        const double rho = sqrt(vv);
+                        const double vl = W.v[nact - 1];
+                        const double gamma = (vl >= 0.0) ? -rho : rho;
+                        const double tau = 1.0 / (rho * (rho + fabs(vl)));
+                        __syncthreads();
+                        if (tid == 0) W.v[nact - 1] = vl - gamma;
+                        __syncthreads();
+                        for (int k = tid; k < nact; k += T) W.d1[k] = tau * W.v[k];
+                        // Q1 v (all rows of Q1) and S v (active rows), then the two rank-1 updates
+                        gt_row_dots(Q1, ldn, n, 0, nact, [](int r_) { return size_t(r_); }, W.v, W.w, W.part);
+                        __syncthreads();
+                        gt_row_dots(S, ldn, nact, 0, nact, [&](int r_) { return size_t(W.rowmap[r_]); }, W.v, W.r, W.part);
+                        __syncthreads();
+                        tile_rc(n, 0, nact - 1, [&](int r_, int c_) { Q1[r_ + size_t(c_) * ldn] -= W.w[r_] * W.d1[c_]; });
+                        tile_rc(nact, 0, nact - 1, [&](int r_, int c_) {
+                            if (r_ != p) S[W.rowmap[r_] + size_t(c_) * ldn] -= W.r[r_] * W.d1[c_];
+                        });
+                        __syncthreads();
+                        if (warp_id() == 0) {
+                            const int lane = lane_id();
+                            for (int base = p; base < nact - 1; base += 32) {
+                                const int k = base + lane;
+                                double uu = 0.0; int ia = 0, rm = 0;
+                                if (k < nact - 1) { uu = W.u[k + 1]; ia = W.iact[k + 1]; rm = W.rowmap[k + 1]; }
+                                __syncwarp();
+                                if (k < nact - 1) { W.u[k] = uu; W.iact[k] = ia; W.rowmap[k] = rm; }
+                                __syncwarp();
+                            }
+                            if (lane == 0) W.rowmap[nact - 1] = prow;
+                        }
+                        __syncthreads();
+                    }
+                    if (tid == 0) {
+                        W.u[nact - 1] = W.u[nact];
+                        W.u[nact] = 0.0;
+                        W.iact[nact - 1] = 0;
+                        W.active[dropped] = 0;
+                    }
+                    --nact;
+                    ++iter1;
+                    __syncthreads();
+                    continue; // label 55
+                }
+            }
+            if (fail != 0) break;
+        }
+    }
+    __syncthreads();
+    // ---- results ---------------------------------------------------------------------------------------------------------------
+    if (B.x) for (int i = tid; i < n; i += T) B.x[(long long)b * n + i] = (fail == 2) ? 0.0 : W.x[i];
+    if (B.iact) for (int i = tid; i < n; i += T) B.iact[(long long)b * n + i] = (i < nact) ? W.iact[i] : 0;
+    if (tid == 0) {
+        if (B.status) B.status[b] = fail;
+        if (B.iters) { B.iters[2LL * b] = iter0; B.iters[2LL * b + 1] = iter1; }
+        if (B.nact) B.nact[b] = nact;
+    }
+    return fail;
+}
+
+// ---- host side (k6_thin.cu) ------------------------------------------------------------------------------------------------
+struct GtPlan {
+    int threads, grid, per_sm, ok;
+    size_t smem_bytes;
+    long long ws_stride; // doubles of global workspace per CTA (Q1 + S)
+};
+GtPlan gt_plan(int n, int meq, int m, int tab_doubles, int batch, int sms, size_t smem_optin);
+size_t gt_factor_smem(int n);
+// factor `count` Hessians Q (n x n each): Jt / JtT receive count * n * n doubles, pd count flags
+cudaError_t gt_factor_launch(DArr Q, int n, int count, double* Jt, double* JtT, int* pd, int sms, cudaStream_t st);
+cudaError_t gt_launch(const GtBatch& B, const GtPlan& plan, cudaStream_t st);
+
+} // namespace cb

@@ -339,7 +339,7 @@ __device__ __forceinline__ void dev_q_chain(const BuildParams& P, int b, int ch,
     const int off = P.initial_state ? P.nx : 0;
     const int a = ch % nu, bb = (ch / nu) % nu, dd = ch / (nu * nu) - (N - 1); // dd = j1 - j2
     const int ad = dd < 0 ? -dd : dd;
-    double* Q = P.Q + (long long)b * nvar * nvar;
+    double* Q = P.Q + (long long)b * P.sQ;
     double run[kMaxCost];
     int done[kMaxCost];
     for (int ci = 0; ci < P.ncost; ++ci) {
@@ -489,7 +489,7 @@ __global__ void k2_assemble_q_tiled_kernel(const __grid_constant__ BuildParams P
     }
     __syncthreads();
     const int off = P.initial_state ? P.nx : 0;
-    double* Q = P.Q + (long long)b * nvar * nvar + off + (long long)off * nvar;
+    double* Q = P.Q + (long long)b * P.sQ + off + (long long)off * nvar;
     if (off == 0 && nvar == nU) {
         for (int idx = threadIdx.x; idx < nU * nU; idx += blockDim.x) Q[idx] = stage_sm[tile + idx];
     } else {
@@ -690,7 +690,7 @@ __device__ __forceinline__ void dev_finalize(const BuildParams& P, int b)
     {
         const double* x0 = P.x0.at(b);
         double* c = P.c + (long long)b * nvar;
-        double* Q = P.Q + (long long)b * nvar * nvar;
+        double* Q = P.Q + (long long)b * P.sQ;
         for (int col = tid; col < nU; col += T) {
             double acc = 0.0;
             for (int ci = 0; ci < P.ncost; ++ci) {
@@ -913,6 +913,7 @@ int k2k4_assemble_launch(const BuildParams& P, double* schur_ws, long long schur
     }
     {
         const int nchain = (2 * P.N - 1) * P.nu * P.nu;
+        const int nbq = P.sQ == 0 ? 1 : nb; // batch-invariant Hessian: assembled once from instance 0's tables
         size_t need = 0; // staged tables: M A^k B blocks + weights of every step-size cost
         for (int i = 0; i < P.ncost; ++i) if (!P.cost[i].dense) need += size_t(P.cost[i].sMGx) + P.cost[i].rows;
         const int staged = need * sizeof(double) <= 40 * 1024;
@@ -921,9 +922,9 @@ int k2k4_assemble_launch(const BuildParams& P, double* schur_ws, long long schur
         const int tiled = staged && (need + tile) * sizeof(double) <= 44 * 1024;
         if (tiled) {
             const int threads = std::min(256, std::max(32, ceil_div(P.N * P.nu * P.nu, 32) * 32));
-            k2_assemble_q_tiled_kernel<<<nb, threads, (need + tile) * sizeof(double), st>>>(P);
+            k2_assemble_q_tiled_kernel<<<nbq, threads, (need + tile) * sizeof(double), st>>>(P);
         } else
-            k2_assemble_q_kernel<<<dim3(ceil_div(nchain, 128), nb), 128, staged ? need * sizeof(double) : 0, st>>>(P, staged);
+            k2_assemble_q_kernel<<<dim3(ceil_div(nchain, 128), nbq), 128, staged ? need * sizeof(double) : 0, st>>>(P, staged);
         CB_CHECK_LAUNCH();
     }
     const long long sPsi = (long long)X * nU, sPhi = (long long)X * nx;
@@ -938,7 +939,7 @@ int k2k4_assemble_launch(const BuildParams& P, double* schur_ws, long long schur
         }
         k2_dense_cost_epilogue_kernel<<<dim3(ceil_div(R * nU, 256), nb), 256, 0, st>>>(P, ci);
         CB_CHECK_LAUNCH();
-        CB_GEMM(1, nU, nU, R, 1.0, F.T, R, F.sT, F.WT, R, F.sT, 1.0, P.Q + off + (long long)off * nvar, nvar, (long long)nvar * nvar, nb, st);
+        CB_GEMM(1, nU, nU, R, 1.0, F.T, R, F.sT, F.WT, R, F.sT, 1.0, P.Q + off + (long long)off * nvar, nvar, P.sQ, nb, st);
         CB_GEMM(1, nx, nU, R, 1.0, F.MPhi, R, F.sMPhi, F.WT, R, F.sT, 0.0, F.E, nx, F.sE, nb, st);
         CB_GEMM(1, 1, nU, R, 1.0, F.res, R, F.sres, F.WT, R, F.sT, 0.0, F.f, 1, F.sf, nb, st);
     }
@@ -972,7 +973,7 @@ int k2k4_assemble_launch(const BuildParams& P, double* schur_ws, long long schur
         k3_dense_cstr_epilogue_kernel<<<dim3(ceil_div(R * nU, 256), nb), 256, 0, st>>>(P, fi);
         CB_CHECK_LAUNCH();
     }
-    if (P.meq + P.mineq > 0) {
+    if (P.meq + P.mineq > 0 && !P.skip_rows) {
         k3_fill_rows_kernel<<<dim3(ceil_div(P.meq + P.mineq, 128), nb), 128, 0, st>>>(P);
         CB_CHECK_LAUNCH();
     }
@@ -1003,6 +1004,15 @@ int k2k4_assemble_launch(const BuildParams& P, double* schur_ws, long long schur
         CB_CHECK_LAUNCH();
     }
     return launches;
+}
+
+int k3_fill_rows_launch(const BuildParams& P, cudaStream_t st)
+{
+    if (P.meq + P.mineq == 0) return 0;
+    if (P.batch > 65535) return -int(cudaErrorInvalidValue);
+    k3_fill_rows_kernel<<<dim3(ceil_div(P.meq + P.mineq, 128), P.batch), 128, 0, st>>>(P);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 1 : -int(e);
 }
 
 int k4_finalize_launch(const BuildParams& P, int sms, cudaStream_t st)
