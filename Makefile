@@ -1,7 +1,8 @@
 # Builds libcopra_b200.so (C ABI + sm_100a kernels) in-tree, and the CPU oracle (test infrastructure).
 NVCC ?= nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v
+EXTRA ?=
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v $(EXTRA)
 CSRC := copra_b200/csrc
 OBJS := $(CSRC)/k6_solver.o $(CSRC)/k6_thin.o $(CSRC)/k1_k7_lmpc.o $(CSRC)/dgemm_dmma.o $(CSRC)/fp64_peak.o $(CSRC)/capi.o
 LIB := copra_b200/lib/libcopra_b200.so

@@ -444,11 +444,17 @@ bool plan_thin(copra_b200_handle* h)
         GtFam& f = T.fam[k];
         f.rows = F.rows; f.i0 = F.i0; f.i1 = F.i1; f.is_eq = F.is_eq; f.row_off = F.row_off;
         f.tab = tab;
-        tab += F.rows * P.nu * (P.N + 1);
+        tab += F.rows * P.nu * ((P.N + 1) | 1);
     }
     T.tab_doubles = tab;
-    h->gtplan = gt_plan(T.n, T.meq, T.m, tab, T.batch, sms, h->smem_optin);
+    T.ldk = (P.N + 1) | 1;
+    T.ld = gt_even(T.n);
+    const char* re = getenv("COPRA_B200_THIN_REORTH");
+    T.reorth = re ? atof(re) : 1e-2;
+    const GtShape shape{ T.n, T.meq, T.m, tab, T.ldk, T.ld };
+    h->gtplan = gt_plan(shape, T.batch, sms, h->smem_optin);
     if (!h->gtplan.ok) return false;
+    T.q1s = h->gtplan.q1s;
     h->use_thin = true;
     return true;
 }
@@ -459,24 +465,24 @@ int run_gt(copra_b200_handle* h, double* x, int* status, int* iters, int* nact, 
     GtBatch& T = h->gt;
     const GtPlan& plan = h->gtplan;
     const int sms = h->sm_limit > 0 ? std::min(h->sm_limit, h->sms) : h->sms;
-    const size_t n = P.nvar, count = P.sQ ? size_t(P.batch) : 1;
+    const size_t n = P.nvar, ldj = size_t(T.ld), count = P.sQ ? size_t(P.batch) : 1;
     int rc;
     double *Jt = nullptr, *JtT = nullptr, *wsp = nullptr;
     int *pd = nullptr, *counter = nullptr;
-    if ((rc = ws(h, "gt_Jt", count * n * n, &Jt))) return rc;
-    if ((rc = ws(h, "gt_JtT", count * n * n, &JtT))) return rc;
+    if ((rc = ws(h, "gt_Jt", count * ldj * n, &Jt))) return rc;
+    if ((rc = ws(h, "gt_JtT", count * ldj * n, &JtT))) return rc;
     if ((rc = ws(h, "gt_pd", count, &pd))) return rc;
     if ((rc = ws(h, "gt_ws", size_t(plan.grid) * plan.ws_stride, &wsp))) return rc;
     if ((rc = ws(h, "counter", 2, &counter))) return rc;
     if (!h->factor_valid) {
-        cudaError_t e = gt_factor_launch(DArr{ P.Q, P.sQ }, P.nvar, int(count), Jt, JtT, pd, sms, h->stream);
+        cudaError_t e = gt_factor_launch(DArr{ P.Q, P.sQ }, P.nvar, T.ld, int(count), Jt, JtT, pd, sms, h->stream);
         if (e != cudaSuccess) return fail(h, COPRA_B200_E_CUDA, "gt_factor_launch: %s", cudaGetErrorString(e));
         h->launches += 1; h->call_launches += 1;
         h->factor_valid = true;
     }
     CU(cudaMemsetAsync(counter, 0, 2 * sizeof(int), h->stream));
     for (int k = 0; k < P.nfam; ++k) { T.fam[k].EGx = P.fam[k].EGx; T.fam[k].sEGx = P.fam[k].sEGx; }
-    const long long nn = (long long)(n * n);
+    const long long nn = (long long)(ldj * n);
     T.Jt = DArr{ Jt, P.sQ ? nn : 0 };
     T.JtT = DArr{ JtT, P.sQ ? nn : 0 };
     T.pd = pd; T.pd_stride = P.sQ ? 1 : 0;

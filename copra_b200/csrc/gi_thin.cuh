@@ -25,6 +25,12 @@
 #include "common.cuh"
 #include "engine.cuh"
 #include "gi_solver.cuh"
+#ifdef GT_PROFILE
+#include <cstdio>
+#define GT_T(k) do { const long long t1_ = clock64(); gt_acc[k] += t1_ - gt_t0; gt_t0 = t1_; } while (0)
+#else
+#define GT_T(k) do { } while (0)
+#endif
 
 namespace cb {
 
@@ -38,6 +44,10 @@ struct GtFam {
 struct GtBatch {
     int n, meq, m, batch;
     int structured, nu, N, nfam, tab_doubles;
+    int ldk;            // row length of the transposed tables in shared memory ((N+1) | 1)
+    int ld;             // leading dimension of Jt, JtT, Q1 (n rounded up to even: 16-byte aligned columns for 128-bit loads)
+    int q1s;            // columns of Q1 held in shared memory (the rest lives in the global workspace)
+    double reorth;      // second Gram-Schmidt pass when |zt|^2 < reorth * |d|^2
     GtFam fam[kMaxFam];
     DArr Jt, JtT;       // R^-1 column-major (entries i <= j of column j) and its transpose (entries j >= i of column i)
     const int* pd;      // 1 = Hessian positive definite, per distinct Hessian
@@ -45,7 +55,7 @@ struct GtBatch {
     DArr c, Aeq, beq, Aineq, bineq, lb, ub;
     double* x;
     int *status, *iters, *nact, *iact;
-    double* ws;         // per CTA: Q1 (n x n, ld n) then S (n x n, ld n)
+    double* ws;         // per CTA: Q1 (ld x n) then S (n x n, ld n)
     long long ws_stride;
     int* counter;
     double vsmall;
@@ -53,33 +63,38 @@ struct GtBatch {
 };
 
 struct GtLayout {
-    size_t oTab, oX, oD, oZt, oZ, oAv, oR, oU, oD1, oW, oV, oLb, oUb, oSl, oB, oNorm, oRed, oPart; // doubles
-    size_t oIact, oRowmap, oRedI, oActive, oSgn, bytes;                                             // bytes
+    size_t oTab, oX, oXt, oD, oZt, oZ, oAv, oR, oU, oD1, oW, oV, oLb, oUb, oSl, oB, oNorm, oRed, oPart, oQ1; // doubles
+    size_t oIact, oRowmap, oRedI, oActive, oSgn, bytes;                                                       // bytes
 };
 
-__host__ __device__ inline GtLayout gt_layout(int n, int meq, int m, int tab_doubles, int threads)
+__host__ __device__ inline int gt_even(int n) { return (n + 1) & ~1; }
+
+// `q1s` columns of Q1 (ld doubles each) are placed right after the vectors
+__host__ __device__ inline GtLayout gt_layout(int n, int meq, int m, int tab_doubles, int threads, int q1s)
 {
     GtLayout L;
-    const int mg = meq + m;
+    const int mg = gt_even(meq + m), np = gt_even(n);
     size_t o = 0;
     L.oTab = o; o += (size_t(tab_doubles) + 1) & ~size_t(1);
-    L.oX = o; o += n;
-    L.oD = o; o += n;
-    L.oZt = o; o += n;
-    L.oZ = o; o += n;
-    L.oAv = o; o += n;
-    L.oR = o; o += n;
-    L.oU = o; o += n + 1;
-    L.oD1 = o; o += n;
-    L.oW = o; o += n;
-    L.oV = o; o += n;
-    L.oLb = o; o += n;
-    L.oUb = o; o += n;
+    L.oX = o; o += np;
+    L.oXt = o; o += np;
+    L.oD = o; o += np;
+    L.oZt = o; o += np;
+    L.oZ = o; o += np;
+    L.oAv = o; o += np;
+    L.oR = o; o += np;
+    L.oU = o; o += np + 2;
+    L.oD1 = o; o += np;
+    L.oW = o; o += np;
+    L.oV = o; o += np;
+    L.oLb = o; o += np;
+    L.oUb = o; o += np;
     L.oSl = o; o += mg;
     L.oB = o; o += mg;
     L.oNorm = o; o += mg;
     L.oRed = o; o += 4 * kMaxWarps;
     L.oPart = o; o += 2 * size_t(threads) + 64;
+    L.oQ1 = o; o += size_t(q1s) * np;
     size_t b = o * sizeof(double);
     L.oIact = b; b += sizeof(int) * size_t(n);
     L.oRowmap = b; b += sizeof(int) * size_t(n);
@@ -91,18 +106,18 @@ __host__ __device__ inline GtLayout gt_layout(int n, int meq, int m, int tab_dou
 }
 
 struct GtWork {
-    double *tab, *x, *d, *zt, *z, *av, *r, *u, *d1, *w, *v, *lb, *ub, *sl, *bv, *norm, *red, *part;
+    double *tab, *x, *xt, *d, *zt, *z, *av, *r, *u, *d1, *w, *v, *lb, *ub, *sl, *bv, *norm, *red, *part;
     int *iact, *rowmap, *redi;
     unsigned char* active;
     signed char* sgn;
-    double *Q1, *S;
+    double *Q1s, *Q1, *S; // Q1s: columns [0, q1s) in shared memory; Q1: global, column c at Q1 + c * ld (c >= q1s used)
 };
 
 __device__ inline GtWork gt_carve(const GtLayout& L, unsigned char* smem, double* ws, int n)
 {
     GtWork W;
     double* base = reinterpret_cast<double*>(smem);
-    W.tab = base + L.oTab; W.x = base + L.oX; W.d = base + L.oD; W.zt = base + L.oZt; W.z = base + L.oZ;
+    W.tab = base + L.oTab; W.x = base + L.oX; W.xt = base + L.oXt; W.d = base + L.oD; W.zt = base + L.oZt; W.z = base + L.oZ;
     W.av = base + L.oAv; W.r = base + L.oR; W.u = base + L.oU; W.d1 = base + L.oD1; W.w = base + L.oW; W.v = base + L.oV;
     W.lb = base + L.oLb; W.ub = base + L.oUb; W.sl = base + L.oSl; W.bv = base + L.oB; W.norm = base + L.oNorm;
     W.red = base + L.oRed; W.part = base + L.oPart;
@@ -111,44 +126,61 @@ __device__ inline GtWork gt_carve(const GtLayout& L, unsigned char* smem, double
     W.redi = reinterpret_cast<int*>(smem + L.oRedI);
     W.active = smem + L.oActive;
     W.sgn = reinterpret_cast<signed char*>(smem + L.oSgn);
+    W.Q1s = base + L.oQ1;
     W.Q1 = ws;
-    W.S = ws + size_t(n) * n;
+    W.S = ws + size_t(gt_even(n)) * n;
     return W;
 }
 
-// ---- triangular mat-vecs against the read-only factor: one warp per output, four outputs and two strides in flight ----
-// out[c] = sum_{k < len(c)} M[base(c) + k] * vec[voff(c) + k],  c in [0, nout)
-template <class FB, class FL, class FO>
-__device__ __forceinline__ void gt_seg_dots(const double* __restrict__ M, int nout, FB base, FL len, FO voff,
+// ---- streaming dot products: one warp per output, four outputs x two 128-bit loads per lane in flight ------------------
+// out[c] = sum_{skip(c) <= k < len(c)} M[base(c) + k] * vec[voff(c) + k],  c in [0, nout); base and voff even (16-byte
+// aligned), M read through the read-only path when NC (the factor), plain loads otherwise (Q1: written by this CTA).
+template <bool NC> __device__ __forceinline__ double2 gt_ld2(const double* p)
+{
+    if (NC) return __ldg(reinterpret_cast<const double2*>(p));
+    return *reinterpret_cast<const double2*>(p);
+}
+
+template <bool NC, class FB, class FL, class FO, class FS>
+__device__ __forceinline__ void gt_seg_dots(const double* __restrict__ M, int c_lo, int c_hi, FB base, FL len, FO voff, FS skip,
     const double* __restrict__ vec, double* __restrict__ out)
 {
     const int lane = lane_id(), wp = warp_id(), nw = blockDim.x >> 5;
-    for (int c = 4 * wp; c < nout; c += 4 * nw) {
+    for (int c = c_lo + 4 * wp; c < c_hi; c += 4 * nw) {
         const double* m[4];
         const double* v[4];
-        int ln[4];
+        int ln[4], sk[4];
         int lmax = 0;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int cc = min(c + u, nout - 1);
+            const int cc = min(c + u, c_hi - 1);
             m[u] = M + base(cc);
             v[u] = vec + voff(cc);
-            ln[u] = (c + u < nout) ? len(cc) : 0;
+            ln[u] = (c + u < c_hi) ? len(cc) : 0;
+            sk[u] = skip(cc);
             lmax = max(lmax, ln[u]);
         }
         double s[4] = { 0.0, 0.0, 0.0, 0.0 };
         double t[4] = { 0.0, 0.0, 0.0, 0.0 };
-        for (int k = lane; k < lmax; k += 64) {
-            double a0[4], a1[4];
+        for (int k = 2 * lane; k < lmax; k += 128) {
+            double2 a0[4], a1[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                a0[u] = (k < ln[u]) ? __ldg(m[u] + k) : 0.0;
-                a1[u] = (k + 32 < ln[u]) ? __ldg(m[u] + k + 32) : 0.0;
+                a0[u] = (k < ln[u]) ? gt_ld2<NC>(m[u] + k) : make_double2(0.0, 0.0);
+                a1[u] = (k + 64 < ln[u]) ? gt_ld2<NC>(m[u] + k + 64) : make_double2(0.0, 0.0);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                if (k < ln[u]) s[u] = fma(a0[u], v[u][k], s[u]);
-                if (k + 32 < ln[u]) t[u] = fma(a1[u], v[u][k + 32], t[u]);
+                if (k < ln[u]) {
+                    const double2 x = *reinterpret_cast<const double2*>(v[u] + k);
+                    if (k >= sk[u]) s[u] = fma(a0[u].x, x.x, s[u]);
+                    if (k + 1 < ln[u]) s[u] = fma(a0[u].y, x.y, s[u]);
+                }
+                if (k + 64 < ln[u]) {
+                    const double2 x = *reinterpret_cast<const double2*>(v[u] + k + 64);
+                    t[u] = fma(a1[u].x, x.x, t[u]);
+                    if (k + 65 < ln[u]) t[u] = fma(a1[u].y, x.y, t[u]);
+                }
             }
         }
 #pragma unroll
@@ -156,26 +188,100 @@ __device__ __forceinline__ void gt_seg_dots(const double* __restrict__ M, int no
             double q = s[u] + t[u];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-            if (lane == 0 && c + u < nout) out[c + u] = q;
+            if (lane == 0 && c + u < c_hi) out[c + u] = q;
         }
     }
 }
 
 // d[j] = sum_{i <= j, i < supp} Jt[i, j] a[i]
-__device__ __forceinline__ void gt_jt_dots(const double* __restrict__ Jt, int n, int supp, const double* __restrict__ a,
+__device__ __forceinline__ void gt_jt_dots(const double* __restrict__ Jt, int n, int ld, int supp, const double* __restrict__ a,
     double* __restrict__ d)
 {
-    gt_seg_dots(Jt, n, [&](int j) { return size_t(j) * n; }, [&](int j) { return min(j + 1, supp); }, [](int) { return 0; }, a, d);
+    gt_seg_dots<true>(Jt, 0, n, [&](int j) { return size_t(j) * ld; }, [&](int j) { return min(j + 1, supp); }, [](int) { return 0; },
+        [](int) { return 0; }, a, d);
 }
-// z[i] = sum_{j >= i} Jt[i, j] v[j]   (JtT[j + i n] = Jt[i, j])
-__device__ __forceinline__ void gt_j_dots(const double* __restrict__ JtT, int n, const double* __restrict__ v, double* __restrict__ z)
+// z[i] = sum_{j >= i} Jt[i, j] v[j]   (JtT[j + i ld] = Jt[i, j]); odd rows start one element early (skipped in the sum)
+__device__ __forceinline__ void gt_j_dots(const double* __restrict__ JtT, int n, int ld, const double* __restrict__ v, double* __restrict__ z)
 {
-    gt_seg_dots(JtT, n, [&](int i) { return size_t(i) * n + i; }, [&](int i) { return n - i; }, [](int i) { return i; }, v, z);
+    gt_seg_dots<true>(JtT, 0, n, [&](int i) { return size_t(i) * ld + (i & ~1); }, [&](int i) { return n - (i & ~1); },
+        [](int i) { return i & ~1; }, [](int i) { return i & 1; }, v, z);
+}
+// out[c] = Q1[:, c] . vec for c in [0, nact): head columns from shared memory, the rest from the global workspace
+__device__ __forceinline__ void gt_q1_col_dots(const GtWork& W, int n, int ld, int q1s, int nact, const double* __restrict__ vec,
+    double* __restrict__ out)
+{
+    const int ns = min(nact, q1s);
+    if (ns > 0)
+        gt_seg_dots<false>(W.Q1s, 0, ns, [&](int c) { return size_t(c) * ld; }, [&](int) { return n; }, [](int) { return 0; },
+            [](int) { return 0; }, vec, out);
+    if (nact > q1s)
+        gt_seg_dots<false>(W.Q1, q1s, nact, [&](int c) { return size_t(c) * ld; }, [&](int) { return n; }, [](int) { return 0; },
+            [](int) { return 0; }, vec, out);
 }
 
-// out[r] = sum_{c in [c0,c1)} M[rowof(r) + c*ld] * vec[c], r in [0, rows): lanes along rows, the column range split over
-// G = T / round32(rows) thread groups when the CTA has more threads than rows; four independent loads in flight per thread.
-// Contains one __syncthreads when the split is active; the caller syncs before reading `out`.
+// out[r] = sum_{c < nact} Q1[r, c] * vec[c]: a thread owns a PAIR of rows (one 128-bit load per column), the column range
+// is split over G = T / round32(ld / 2) thread groups whose partial sums meet in `part` (fixed order).  One __syncthreads
+// inside when G > 1; the caller syncs before reading `out`.
+__device__ __forceinline__ void gt_q1_row_dots(const GtWork& W, int ld, int q1s, int nact, const double* __restrict__ vec,
+    double* __restrict__ out, double* __restrict__ part)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int pairs = ld >> 1, rp = max(32, round32(pairs));
+    const int G = max(1, T / rp);
+    if (T < rp) { // more row pairs than threads: loop over pairs, all columns per thread
+        for (int pr = tid; pr < pairs; pr += T) {
+            double sx = 0.0, sy = 0.0;
+            for (int c = 0; c < nact; ++c) {
+                const double* col = (c < q1s ? W.Q1s : W.Q1) + size_t(c) * ld;
+                const double2 a = *reinterpret_cast<const double2*>(col + 2 * pr);
+                sx = fma(a.x, vec[c], sx);
+                sy = fma(a.y, vec[c], sy);
+            }
+            out[2 * pr] = sx;
+            out[2 * pr + 1] = sy;
+        }
+        return;
+    }
+    const int g = tid / rp, pr = tid - g * rp;
+    double sx0 = 0.0, sy0 = 0.0, sx1 = 0.0, sy1 = 0.0;
+    if (g < G && pr < pairs) {
+        int c = g;
+        for (; c + G < nact; c += 2 * G) {
+            const double* col0 = (c < q1s ? W.Q1s : W.Q1) + size_t(c) * ld;
+            const double* col1 = (c + G < q1s ? W.Q1s : W.Q1) + size_t(c + G) * ld;
+            const double2 a = *reinterpret_cast<const double2*>(col0 + 2 * pr);
+            const double2 e = *reinterpret_cast<const double2*>(col1 + 2 * pr);
+            sx0 = fma(a.x, vec[c], sx0);
+            sy0 = fma(a.y, vec[c], sy0);
+            sx1 = fma(e.x, vec[c + G], sx1);
+            sy1 = fma(e.y, vec[c + G], sy1);
+        }
+        if (c < nact) {
+            const double* col0 = (c < q1s ? W.Q1s : W.Q1) + size_t(c) * ld;
+            const double2 a = *reinterpret_cast<const double2*>(col0 + 2 * pr);
+            sx0 = fma(a.x, vec[c], sx0);
+            sy0 = fma(a.y, vec[c], sy0);
+        }
+    }
+    if (G == 1) {
+        if (pr < pairs) { out[2 * pr] = sx0 + sx1; out[2 * pr + 1] = sy0 + sy1; }
+        return;
+    }
+    if (g < G && pr < pairs) {
+        part[2 * (g * rp + pr)] = sx0 + sx1;
+        part[2 * (g * rp + pr) + 1] = sy0 + sy1;
+    }
+    __syncthreads();
+    if (tid < pairs) {
+        double ax = part[2 * tid], ay = part[2 * tid + 1];
+        for (int k = 1; k < G; ++k) { ax += part[2 * (k * rp + tid)]; ay += part[2 * (k * rp + tid) + 1]; }
+        out[2 * tid] = ax;
+        out[2 * tid + 1] = ay;
+    }
+}
+
+// out[r] = sum_{c in [c0,c1)} M[rowof(r) + c*ld] * vec[c], r in [0, rows) -- the S mat-vecs (rows through rowmap).
+// Lanes along rows, the column range split over G = T / round32(rows) thread groups; one __syncthreads when G > 1.
 template <class FR>
 __device__ __forceinline__ void gt_row_dots(const double* __restrict__ M, size_t ld, int rows, int c0, int c1, FR rowof,
     const double* __restrict__ vec, double* __restrict__ out, double* __restrict__ part)
@@ -222,13 +328,19 @@ __device__ __forceinline__ void gt_row_dots(const double* __restrict__ M, size_t
 }
 
 // ---- structured general rows -------------------------------------------------------------------------------------------
-// sl[row] = sum_{j <= min(i, N-1)} sum_bb T[l + r (bb + nu (i - j))] x[j nu + bb]   for every row (family, step i, line l).
-// One warp per (4 steps x 4 lines) tile: the lanes split the kk = i - j range, keep 16 accumulators and meet in a
-// 16-shuffle transpose-reduction; fixed summation order (deterministic).
+// sl[row] = sum_{j <= min(i, N-1)} sum_bb T[line, bb, i - j] x[j nu + bb]   for every row (family, step i, line).
+// One warp per (4 steps x 4 lines) tile: the lanes split the kk = i - j range -- the tables are stored kk-fastest and x is
+// de-interleaved per input (xt[bb N + j]) so that every shared-memory load of a warp is a run of consecutive words -- keep
+// 16 accumulators and meet in a 16-shuffle transpose-reduction; fixed summation order (deterministic).
 __device__ __forceinline__ void gt_products(const GtBatch& B, const GtWork& W)
 {
-    const int nu = B.nu, N = B.N;
+    const int nu = B.nu, N = B.N, ldk = B.ldk;
     const int lane = lane_id(), wp = warp_id(), nw = blockDim.x >> 5;
+    for (int k = threadIdx.x; k < B.n; k += blockDim.x) {
+        const int j = k / nu, bb = k - j * nu;
+        W.xt[bb * N + j] = W.x[k];
+    }
+    __syncthreads();
     int task0 = 0;
     for (int fi = 0; fi < B.nfam; ++fi) {
         const GtFam& F = B.fam[fi];
@@ -238,7 +350,6 @@ __device__ __forceinline__ void gt_products(const GtBatch& B, const GtWork& W)
         double* out = W.sl + (F.is_eq ? 0 : B.meq) + F.row_off;
         int t = (wp - task0 % nw + nw) % nw;
         for (; t < ntask; t += nw) {
-            // long tiles (late steps) first within a warp's list does not matter: cyclic deal balances well enough
             const int sb = nsb - 1 - t / nrg, rg = t % nrg;
             const int ib = F.i0 + 4 * sb, l0 = 4 * rg;
             const int kk_lo = max(0, ib - (N - 1)), kk_hi = min(ib + 3, F.i1 - 1);
@@ -247,19 +358,20 @@ __device__ __forceinline__ void gt_products(const GtBatch& B, const GtWork& W)
             for (int k = 0; k < 16; ++k) acc[k] = 0.0;
             for (int kk = kk_lo + lane; kk <= kk_hi; kk += 32) {
                 for (int bb = 0; bb < nu; ++bb) {
-                    const double* tp = tab + l0 + r * (bb + nu * kk);
+                    const double* tp = tab + size_t(l0 + r * bb) * ldk + kk;
+                    const double* xp = W.xt + bb * N + (ib - kk);
                     double tv[4], xv[4];
 #pragma unroll
-                    for (int ll = 0; ll < 4; ++ll) tv[ll] = (l0 + ll < r) ? tp[ll] : 0.0;
+                    for (int ll = 0; ll < 4; ++ll) tv[ll] = (l0 + ll < r) ? tp[size_t(ll) * ldk] : 0.0;
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) {
-                        const int j = ib + s - kk;
-                        xv[s] = (j >= 0 && j < N && ib + s < F.i1) ? W.x[j * nu + bb] : 0.0;
+                    for (int s_ = 0; s_ < 4; ++s_) {
+                        const int j = ib + s_ - kk;
+                        xv[s_] = (j >= 0 && j < N && ib + s_ < F.i1) ? xp[s_] : 0.0;
                     }
 #pragma unroll
-                    for (int s = 0; s < 4; ++s)
+                    for (int s_ = 0; s_ < 4; ++s_)
 #pragma unroll
-                        for (int ll = 0; ll < 4; ++ll) acc[4 * s + ll] = fma(tv[ll], xv[s], acc[4 * s + ll]);
+                        for (int ll = 0; ll < 4; ++ll) acc[4 * s_ + ll] = fma(tv[ll], xv[s_], acc[4 * s_ + ll]);
                 }
             }
             // transpose-reduce: afterwards lane 2e (e = 0..15) holds the total of acc[e]
@@ -278,8 +390,8 @@ __device__ __forceinline__ void gt_products(const GtBatch& B, const GtWork& W)
             }
             acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
             if ((lane & 1) == 0) {
-                const int e = lane >> 1, s = e >> 2, ll = e & 3;
-                if (ib + s < F.i1 && l0 + ll < r) out[(ib + s - F.i0) * r + l0 + ll] = acc[0];
+                const int e = lane >> 1, s_ = e >> 2, ll = e & 3;
+                if (ib + s_ < F.i1 && l0 + ll < r) out[(ib + s_ - F.i0) * r + l0 + ll] = acc[0];
             }
         }
         task0 += ntask;
@@ -301,47 +413,51 @@ __device__ __forceinline__ void gt_locate(const GtBatch& B, int g, int& fi, int&
     line = (lrow - F.row_off) % F.rows;
 }
 
-// entry k of general row (family F, step, line)
-__device__ __forceinline__ double gt_row_entry(const GtBatch& B, const double* tab, const GtFam& F, int step, int line, int k)
+// table entry (line, input bb, lag kk) of family F in the transposed shared-memory layout
+__device__ __forceinline__ double gt_tab(const GtBatch& B, const double* tab, const GtFam& F, int line, int bb, int kk)
 {
-    const int j = k / B.nu, bb = k - j * B.nu, kk = step - j;
-    return (kk >= 0) ? tab[F.tab + line + F.rows * (bb + B.nu * kk)] : 0.0;
+    return tab[F.tab + size_t(line + F.rows * bb) * B.ldk + kk];
 }
 
 // ---- the solver ----------------------------------------------------------------------------------------------------------
 __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double vsmall, int max_iter)
 {
-    const int n = B.n, meq = B.meq, m = B.m, mg = meq + m, q = mg + 2 * n;
+    const int n = B.n, meq = B.meq, m = B.m, mg = meq + m, q = mg + 2 * n, np = gt_even(n);
     const int tid = threadIdx.x, T = blockDim.x;
+    const int ld = B.ld, q1s = B.q1s;
     const size_t ldn = size_t(n);
     const double* __restrict__ Jt = B.Jt.at(b);
     const double* __restrict__ JtT = B.JtT.at(b);
-    double* __restrict__ Q1 = W.Q1;
     double* __restrict__ S = W.S;
     double* scal = W.red + 2 * kMaxWarps;
     const double* gc = B.c.at(b);
     const double* gAeq = B.Aeq.p ? B.Aeq.at(b) : nullptr;
     const double* gAin = B.Aineq.p ? B.Aineq.at(b) : nullptr;
+    auto q1col = [&](int c) -> double* { return (c < q1s ? W.Q1s : W.Q1) + size_t(c) * ld; };
 
     // ---- 0. load ----------------------------------------------------------------------------------------------------------
     if (B.structured) {
         for (int fi = 0; fi < B.nfam; ++fi) {
             const GtFam& F = B.fam[fi];
             const double* src = F.EGx + (long long)b * F.sEGx;
-            const int cnt = F.rows * B.nu * (B.N + 1);
-            for (int t = tid; t < cnt; t += T) W.tab[F.tab + t] = src[t];
+            const int rn = F.rows * B.nu, cnt = rn * (B.N + 1);
+            for (int t = tid; t < cnt; t += T) {
+                const int kk = t / rn, rem = t - kk * rn; // rem = line + rows * bb
+                W.tab[F.tab + size_t(rem) * B.ldk + kk] = src[t];
+            }
         }
     }
     {
         const double* glb = B.lb.at(b);
         const double* gub = B.ub.at(b);
-        for (int i = tid; i < n; i += T) {
-            W.av[i] = -gc[i];
-            W.lb[i] = glb[i];
-            W.ub[i] = gub[i];
+        for (int i = tid; i < np; i += T) {
+            const bool in = i < n;
+            W.av[i] = in ? -gc[i] : 0.0;
+            W.lb[i] = in ? glb[i] : 0.0;
+            W.ub[i] = in ? gub[i] : 0.0;
             W.u[i] = 0.0;
-            W.iact[i] = 0;
-            W.rowmap[i] = i;
+            W.x[i] = W.d[i] = W.zt[i] = W.z[i] = W.d1[i] = W.w[i] = W.v[i] = W.r[i] = 0.0;
+            if (in) { W.iact[i] = 0; W.rowmap[i] = i; }
         }
         if (tid == 0) W.u[n] = 0.0;
         const double* gbe = meq ? B.beq.at(b) : nullptr;
@@ -354,10 +470,15 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
 
     int fail = 0, nact = 0, iter0 = 0, iter1 = 0;
     if (B.pd[(long long)b * B.pd_stride] == 0) fail = 2;
+#ifdef GT_PROFILE
+    long long gt_acc[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+    long long gt_t0 = clock64();
+    int gt_reorth = 0;
+#endif
 
     if (fail == 0) {
         // ---- unconstrained minimiser x = Jt Jt' (-c) -------------------------------------------------------------------------
-        gt_jt_dots(Jt, n, n, W.av, W.d);
+        gt_jt_dots(Jt, n, ld, n, W.av, W.d);
         // ---- norms of the general rows (the reference's summation order: columns ascending) ---------------------------------
         for (int i = tid; i < mg; i += T) {
             double s = 0.0;
@@ -368,7 +489,7 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
                 const int jmax = min(step, B.N - 1);
                 for (int j = 0; j <= jmax; ++j)
                     for (int bb = 0; bb < B.nu; ++bb) {
-                        const double v = W.tab[F.tab + line + F.rows * (bb + B.nu * (step - j))];
+                        const double v = gt_tab(B, W.tab, F, line, bb, step - j);
                         s += v * v;
                     }
             } else if (i < meq) {
@@ -379,8 +500,9 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
             W.norm[i] = sqrt(s);
         }
         __syncthreads();
-        gt_j_dots(JtT, n, W.d, W.x);
+        gt_j_dots(JtT, n, ld, W.d, W.x);
         __syncthreads();
+        GT_T(0);
 
         // ---- dual active-set iterations ----------------------------------------------------------------------------------------
         for (;;) {
@@ -396,6 +518,7 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
                 }
             }
             __syncthreads();
+            GT_T(1);
             MinIdx best; best.v = 0.0; best.i = -1;
             double best_s = 0.0;
             for (int i = tid; i < q; i += T) {
@@ -424,6 +547,7 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
             if (best.i == nvl) scal[0] = best_s;
             __syncthreads();
             double s_nvl = scal[0];
+            GT_T(2);
 
             // the signed normal a_nvl (quadprog orientation a'x >= b) and d = Jt' a: they do not change at label 55
             int bj = -1, supp = n;
@@ -435,41 +559,48 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
                     gt_locate(B, nvl, fi, step, line);
                     const GtFam& F = B.fam[fi];
                     supp = min(step + 1, B.N) * B.nu;
-                    for (int k = tid; k < n; k += T) W.av[k] = (k < supp) ? sg * gt_row_entry(B, W.tab, F, step, line, k) : 0.0;
+                    for (int k = tid; k < np; k += T) {
+                        const int j = k / B.nu, bb = k - j * B.nu;
+                        W.av[k] = (k < supp) ? sg * gt_tab(B, W.tab, F, line, bb, step - j) : 0.0;
+                    }
                 } else if (nvl < meq) {
                     for (int k = tid; k < n; k += T) W.av[k] = sg * gAeq[nvl + size_t(k) * meq];
                 } else {
                     for (int k = tid; k < n; k += T) W.av[k] = sg * gAin[(nvl - meq) + size_t(k) * m];
                 }
                 __syncthreads();
-                gt_jt_dots(Jt, n, supp, W.av, W.d);
+                gt_jt_dots(Jt, n, ld, supp, W.av, W.d);
             } else {
                 const int j = nvl - mg;
                 if (j < n) { bj = j; bsign = -1.0; }
                 else { bj = j - n; bsign = 1.0; }
                 // d[j] = bsign * Jt[bj, j] (j >= bj): a contiguous run of the transposed factor
-                for (int k = tid; k < n; k += T) W.d[k] = (k >= bj) ? bsign * __ldg(JtT + size_t(bj) * n + k) : 0.0;
+                for (int k = tid; k < n; k += T) W.d[k] = (k >= bj) ? bsign * __ldg(JtT + size_t(bj) * ld + k) : 0.0;
             }
             __syncthreads();
             double dnorm2 = 0.0;
             for (int k = tid; k < n; k += T) dnorm2 += W.d[k] * W.d[k];
             dnorm2 = block_sum(dnorm2, W.red);
+            GT_T(3);
 
             for (;;) { // label 55
                 // d1 = Q1' d ; zt = d - Q1 d1 (second pass when most of d cancelled: "twice is enough")
                 double dd = dnorm2;
                 if (nact > 0) {
-                    col_dots(Q1, int(ldn), n, 0, nact, W.d, W.d1);
+                    gt_q1_col_dots(W, n, ld, q1s, nact, W.d, W.d1);
                     __syncthreads();
-                    gt_row_dots(Q1, ldn, n, 0, nact, [](int r_) { return size_t(r_); }, W.d1, W.w, W.part);
+                    gt_q1_row_dots(W, ld, q1s, nact, W.d1, W.w, W.part);
                     __syncthreads();
                     double acc = 0.0;
                     for (int k = tid; k < n; k += T) { const double v = W.d[k] - W.w[k]; W.zt[k] = v; acc += v * v; }
                     dd = block_sum(acc, W.red);
-                    if (dd < 0.25 * dnorm2) {
-                        col_dots(Q1, int(ldn), n, 0, nact, W.zt, W.v);
+                    if (dd < B.reorth * dnorm2) {
+#ifdef GT_PROFILE
+                        ++gt_reorth;
+#endif
+                        gt_q1_col_dots(W, n, ld, q1s, nact, W.zt, W.v);
                         __syncthreads();
-                        gt_row_dots(Q1, ldn, n, 0, nact, [](int r_) { return size_t(r_); }, W.v, W.w, W.part);
+                        gt_q1_row_dots(W, ld, q1s, nact, W.v, W.w, W.part);
                         __syncthreads();
                         acc = 0.0;
                         for (int k = tid; k < n; k += T) { const double v = W.zt[k] - W.w[k]; W.zt[k] = v; acc += v * v; }
@@ -480,10 +611,12 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
                     for (int k = tid; k < n; k += T) W.zt[k] = W.d[k];
                     __syncthreads();
                 }
+                GT_T(4);
                 // z = Jt zt ; r = S d1
-                gt_j_dots(JtT, n, W.zt, W.z);
+                gt_j_dots(JtT, n, ld, W.zt, W.z);
                 if (nact > 0) gt_row_dots(S, ldn, nact, 0, nact, [&](int r_) { return size_t(W.rowmap[r_]); }, W.d1, W.r, W.part);
                 __syncthreads();
+                GT_T(5);
                 MinIdx tc; tc.v = 0.0; tc.i = -1;
                 for (int i = tid; i < nact; i += T) {
                     if (W.iact[i] - 1 >= meq && W.r[i] > 0.0) {
@@ -520,8 +653,8 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
                     if (t2min) {
                         // ---- add constraint nvl: Q1 gains zt / delta, S the column [-r/delta ; 1/delta] ----------------------
                         const double delta = sqrt(dd), inv = 1.0 / delta;
-                        double* qc = Q1 + size_t(nact) * ldn;
-                        for (int j = tid; j < n; j += T) qc[j] = W.zt[j] * inv;
+                        double* qc = q1col(nact);
+                        for (int j = tid; j < np; j += T) qc[j] = (j < n) ? W.zt[j] * inv : 0.0;
                         const int newrow = W.rowmap[nact];
                         for (int i = tid; i < nact; i += T) {
                             S[W.rowmap[i] + size_t(nact) * ldn] = -W.r[i] * inv;
@@ -534,6 +667,7 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
                         }
                         ++nact;
                         __syncthreads();
+                        GT_T(6);
                         break; // next outer iteration
                     } else {
                         // partial step: refresh s_nvl at the new x (with the equality sign rule)
@@ -549,7 +683,7 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
                             else s = acc + W.bv[nvl];
                         }
                         if (nvl < meq) {
-                            // the sign flip of an equality changes the orientation of a_nvl, hence of d: redo from the top
+                            // the sign flip of an equality changes the orientation of a_nvl, hence of d
                             __syncthreads();
                             if (s > 0.0) {
                                 if (tid == 0) W.sgn[nvl] = -W.sgn[nvl];
@@ -580,11 +714,11 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
                         __syncthreads();
                         for (int k = tid; k < nact; k += T) W.d1[k] = tau * W.v[k];
                         // Q1 v (all rows of Q1) and S v (active rows), then the two rank-1 updates
-                        gt_row_dots(Q1, ldn, n, 0, nact, [](int r_) { return size_t(r_); }, W.v, W.w, W.part);
+                        gt_q1_row_dots(W, ld, q1s, nact, W.v, W.w, W.part);
                         __syncthreads();
                         gt_row_dots(S, ldn, nact, 0, nact, [&](int r_) { return size_t(W.rowmap[r_]); }, W.v, W.r, W.part);
                         __syncthreads();
-                        tile_rc(n, 0, nact - 1, [&](int r_, int c_) { Q1[r_ + size_t(c_) * ldn] -= W.w[r_] * W.d1[c_]; });
+                        tile_rc(n, 0, nact - 1, [&](int r_, int c_) { q1col(c_)[r_] -= W.w[r_] * W.d1[c_]; });
                         tile_rc(nact, 0, nact - 1, [&](int r_, int c_) {
                             if (r_ != p) S[W.rowmap[r_] + size_t(c_) * ldn] -= W.r[r_] * W.d1[c_];
                         });
@@ -612,6 +746,7 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
                     --nact;
                     ++iter1;
                     __syncthreads();
+                    GT_T(7);
                     continue; // label 55
                 }
             }
@@ -619,6 +754,11 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
         }
     }
     __syncthreads();
+#ifdef GT_PROFILE
+    if (tid == 0 && (b % 97) == 0)
+        printf("GTPROF b=%d n=%d iters=%d drops=%d nact=%d reorth=%d | init %lld prod %lld sel %lld normal+Jt'a %lld q1 %lld Jz+S %lld step+add %lld drop %lld\n",
+            b, n, iter0, iter1, nact, gt_reorth, gt_acc[0], gt_acc[1], gt_acc[2], gt_acc[3], gt_acc[4], gt_acc[5], gt_acc[6], gt_acc[7]);
+#endif
     // ---- results ---------------------------------------------------------------------------------------------------------------
     if (B.x) for (int i = tid; i < n; i += T) B.x[(long long)b * n + i] = (fail == 2) ? 0.0 : W.x[i];
     if (B.iact) for (int i = tid; i < n; i += T) B.iact[(long long)b * n + i] = (i < nact) ? W.iact[i] : 0;
@@ -632,14 +772,15 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
 
 // ---- host side (k6_thin.cu) ------------------------------------------------------------------------------------------------
 struct GtPlan {
-    int threads, grid, per_sm, ok;
+    int threads, grid, per_sm, ok, q1s;
     size_t smem_bytes;
     long long ws_stride; // doubles of global workspace per CTA (Q1 + S)
 };
-GtPlan gt_plan(int n, int meq, int m, int tab_doubles, int batch, int sms, size_t smem_optin);
+struct GtShape { int n, meq, m, tab_doubles, ldk, ld; };
+GtPlan gt_plan(const GtShape& s, int batch, int sms, size_t smem_optin);
 size_t gt_factor_smem(int n);
 // factor `count` Hessians Q (n x n each): Jt / JtT receive count * n * n doubles, pd count flags
-cudaError_t gt_factor_launch(DArr Q, int n, int count, double* Jt, double* JtT, int* pd, int sms, cudaStream_t st);
+cudaError_t gt_factor_launch(DArr Q, int n, int ld, int count, double* Jt, double* JtT, int* pd, int sms, cudaStream_t st);
 cudaError_t gt_launch(const GtBatch& B, const GtPlan& plan, cudaStream_t st);
 
 } // namespace cb

@@ -11,38 +11,43 @@ namespace cb {
 // Jt = R^-1 (Q = R'R) for `count` Hessians, one CTA each (blocked DMMA Cholesky + inverse of gi_factor.cuh working in
 // global memory / L2), plus the transposed copy the row-oriented mat-vec reads.  pd[h] = 0 when Q is not positive
 // definite (QuadProg's fail code 2).
-__global__ void __launch_bounds__(512, 1) gt_factor_kernel(DArr Q, int n, int count, double* __restrict__ Jt, double* __restrict__ JtT,
-    int* __restrict__ pd)
+__global__ void __launch_bounds__(512, 1) gt_factor_kernel(DArr Q, int n, int ld, int count, double* __restrict__ Jt,
+    double* __restrict__ JtT, int* __restrict__ pd)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     double* scratch = reinterpret_cast<double*>(smem);
     const int tid = threadIdx.x, T = blockDim.x;
+    const size_t sz = size_t(ld) * n;
     for (int h = blockIdx.x; h < count; h += gridDim.x) {
-        double* J = Jt + (long long)h * n * n;
-        double* JT = JtT + (long long)h * n * n;
+        double* J = Jt + (long long)h * sz;
+        double* JT = JtT + (long long)h * sz;
         const double* q = Q.at(h);
         __syncthreads();
-        for (int idx = tid; idx < n * n; idx += T) J[idx] = q[idx];
+        for (size_t idx = tid; idx < sz; idx += T) {
+            const int i = int(idx % ld), j = int(idx / ld);
+            J[idx] = (i < n) ? q[i + size_t(j) * n] : 0.0;
+            JT[idx] = 0.0;
+        }
         __syncthreads();
-        const bool ok = gi_factor_blocked(J, n, n, scratch);
+        const bool ok = gi_factor_blocked(J, ld, n, scratch);
         __syncthreads();
         if (tid == 0) pd[h] = ok ? 1 : 0;
         if (!ok) continue;
-        // transpose through 32 x 32 tiles (scratch holds >= 33 * 32 doubles: gi_factor_scratch(n) >= 16 n)
+        // transpose through 32 x 32 tiles (scratch holds >= 33 * 32 doubles)
         double* tile = scratch;
         const int nt = (n + 31) >> 5;
         for (int t = 0; t < nt * nt; ++t) {
             const int ti = t % nt, tj = t / nt; // tile rows ti*32.., cols tj*32..
-            if (ti > tj) continue;              // strictly lower tiles are zero and never read
+            if (ti > tj) continue;              // strictly lower tiles are zero
             __syncthreads();
             for (int e = tid; e < 1024; e += T) {
                 const int i = ti * 32 + (e & 31), j = tj * 32 + (e >> 5);
-                tile[(e >> 5) * 33 + (e & 31)] = (i < n && j < n) ? J[i + size_t(j) * n] : 0.0;
+                tile[(e >> 5) * 33 + (e & 31)] = (i < n && j < n) ? J[i + size_t(j) * ld] : 0.0;
             }
             __syncthreads();
             for (int e = tid; e < 1024; e += T) {
                 const int j = tj * 32 + (e & 31), i = ti * 32 + (e >> 5);
-                if (i < n && j < n) JT[j + size_t(i) * n] = tile[(e & 31) * 33 + (e >> 5)];
+                if (i < n && j < n) JT[j + size_t(i) * ld] = tile[(e & 31) * 33 + (e >> 5)];
             }
         }
     }
@@ -53,7 +58,7 @@ __global__ void __launch_bounds__(MAXT, MINB) gi_thin_kernel(const __grid_consta
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_next;
-    const GtLayout L = gt_layout(B.n, B.meq, B.m, B.tab_doubles, blockDim.x);
+    const GtLayout L = gt_layout(B.n, B.meq, B.m, B.tab_doubles, blockDim.x, B.q1s);
     GtWork W = gt_carve(L, smem, B.ws + (long long)blockIdx.x * B.ws_stride, B.n);
     for (;;) {
         if (threadIdx.x == 0) s_next = atomicAdd(B.counter, 1);
@@ -72,30 +77,38 @@ static int gt_env_int(const char* name, int dflt)
     return e ? atoi(e) : dflt;
 }
 
-GtPlan gt_plan(int n, int meq, int m, int tab_doubles, int batch, int sms, size_t smem_optin)
+GtPlan gt_plan(const GtShape& sh, int batch, int sms, size_t smem_optin)
 {
     GtPlan p{};
     p.threads = gt_env_int("COPRA_B200_THIN_THREADS", 512);
     if (p.threads != 256 && p.threads != 512 && p.threads != 1024) p.threads = 512;
-    p.smem_bytes = gt_layout(n, meq, m, tab_doubles, p.threads).bytes;
-    p.ok = p.smem_bytes + 2048 <= smem_optin;
-    int per_sm = int(std::max<size_t>(1, (smem_optin + 1024) / (p.smem_bytes + 1024)));
+    const size_t base = gt_layout(sh.n, sh.meq, sh.m, sh.tab_doubles, p.threads, 0).bytes;
+    p.ok = base + 2048 <= smem_optin;
+    if (!p.ok) return p;
+    // one CTA per SM; whatever shared memory the vectors and tables leave holds the head columns of Q1
+    int per_sm = std::max(1, gt_env_int("COPRA_B200_THIN_CTAS_PER_SM", 1));
     per_sm = std::min(per_sm, 2048 / p.threads);
-    per_sm = std::min(per_sm, std::max(1, gt_env_int("COPRA_B200_THIN_CTAS_PER_SM", p.threads >= 1024 ? 1 : 2)));
+    per_sm = std::min<int>(per_sm, int((smem_optin + 1024) / (base + 1024)));
+    const size_t budget = (smem_optin + 1024) / per_sm - 1024 - 1024; // per CTA, minus static shared memory headroom
+    int q1s = budget > base ? int((budget - base) / (size_t(sh.ld) * sizeof(double))) : 0;
+    q1s = std::min(q1s, sh.n);
+    q1s = std::min(q1s, std::max(0, gt_env_int("COPRA_B200_THIN_Q1S", sh.n)));
+    p.q1s = q1s;
+    p.smem_bytes = gt_layout(sh.n, sh.meq, sh.m, sh.tab_doubles, p.threads, q1s).bytes;
     p.per_sm = per_sm;
     p.grid = std::max(1, std::min(batch, sms * per_sm));
-    p.ws_stride = 2LL * n * n;
+    p.ws_stride = (long long)sh.ld * sh.n + (long long)sh.n * sh.n;
     return p;
 }
 
 size_t gt_factor_smem(int n) { return std::max<size_t>(gi_factor_scratch(n), 33 * 32) * sizeof(double); }
 
-cudaError_t gt_factor_launch(DArr Q, int n, int count, double* Jt, double* JtT, int* pd, int sms, cudaStream_t st)
+cudaError_t gt_factor_launch(DArr Q, int n, int ld, int count, double* Jt, double* JtT, int* pd, int sms, cudaStream_t st)
 {
     const size_t smem = gt_factor_smem(n);
     cudaError_t e = cudaFuncSetAttribute(gt_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    gt_factor_kernel<<<std::max(1, std::min(count, sms)), 512, smem, st>>>(Q, n, count, Jt, JtT, pd);
+    gt_factor_kernel<<<std::max(1, std::min(count, sms)), 512, smem, st>>>(Q, n, ld, count, Jt, JtT, pd);
     return cudaGetLastError();
 }
 
