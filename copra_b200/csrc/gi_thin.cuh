@@ -93,7 +93,7 @@ __host__ __device__ inline GtLayout gt_layout(int n, int meq, int m, int tab_dou
     L.oB = o; o += mg;
     L.oNorm = o; o += mg;
     L.oRed = o; o += 4 * kMaxWarps;
-    L.oPart = o; o += 2 * size_t(threads) + 64;
+    L.oPart = o; o += (size_t(2 * (threads / 32) + (n + 63) / 64 + 2) << 6) + 2 * size_t(threads);
     L.oQ1 = o; o += size_t(q1s) * np;
     size_t b = o * sizeof(double);
     L.oIact = b; b += sizeof(int) * size_t(n);
@@ -132,91 +132,115 @@ __device__ inline GtWork gt_carve(const GtLayout& L, unsigned char* smem, double
     return W;
 }
 
-// ---- streaming dot products: one warp per output, four outputs x two 128-bit loads per lane in flight ------------------
-// out[c] = sum_{skip(c) <= k < len(c)} M[base(c) + k] * vec[voff(c) + k],  c in [0, nout); base and voff even (16-byte
-// aligned), M read through the read-only path when NC (the factor), plain loads otherwise (Q1: written by this CTA).
-template <bool NC> __device__ __forceinline__ double2 gt_ld2(const double* p)
-{
-    if (NC) return __ldg(reinterpret_cast<const double2*>(p));
-    return *reinterpret_cast<const double2*>(p);
-}
-
-template <bool NC, class FB, class FL, class FO, class FS>
-__device__ __forceinline__ void gt_seg_dots(const double* __restrict__ M, int c_lo, int c_hi, FB base, FL len, FO voff, FS skip,
-    const double* __restrict__ vec, double* __restrict__ out)
+// ---- triangular mat-vecs against the read-only factor ---------------------------------------------------------------
+// y = M x restricted to a trapezoid of a column-major matrix: rows are cut into chunks of 64 (a lane owns a PAIR of rows:
+// one 128-bit load per column, no predicate, no shuffle), chunk k sums the columns [clo(k), chi(k)).  The (chunk, column
+// slice) pairs form a static task list dealt to the warps; partial sums meet in `part` in task order (deterministic).
+//   ZMODE : z[i] = sum_{j >= i} Jt[i, j] v[j]      on M = Jt  : clo = 64 k, chi = n      (stored zeros below the diagonal)
+//   !ZMODE: d[j] = sum_{i <= j, i < supp} Jt[i, j] a[i]  on M = JtT : clo = 0, chi = min(64 k + 64, supp)
+// Contains one __syncthreads; the caller syncs before reading `out`.
+template <bool ZMODE>
+__device__ __forceinline__ void gt_trap_mv(const double* __restrict__ M, int ld, int n, int supp, const double* __restrict__ vec,
+    double* __restrict__ out, double* __restrict__ part)
 {
     const int lane = lane_id(), wp = warp_id(), nw = blockDim.x >> 5;
-    for (int c = c_lo + 4 * wp; c < c_hi; c += 4 * nw) {
-        const double* m[4];
-        const double* v[4];
-        int ln[4], sk[4];
-        int lmax = 0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int cc = min(c + u, c_hi - 1);
-            m[u] = M + base(cc);
-            v[u] = vec + voff(cc);
-            ln[u] = (c + u < c_hi) ? len(cc) : 0;
-            sk[u] = skip(cc);
-            lmax = max(lmax, ln[u]);
+    const int nc = (n + 63) >> 6;
+    auto clo = [&](int k) { return ZMODE ? (k << 6) : 0; };
+    auto chi = [&](int k) { return ZMODE ? n : min(min((k << 6) + 64, supp), n); };
+    int tot = 0;
+    for (int k = 0; k < nc; ++k) tot += chi(k) - clo(k);
+    const int cw = max(64, (((tot + 2 * nw - 1) / (2 * nw)) + 63) & ~63); // columns per task
+    int ntask = 0;
+    for (int k = 0; k < nc; ++k) ntask += (chi(k) - clo(k) + cw - 1) / cw;
+    for (int t = wp; t < ntask; t += nw) {
+        int k = 0, t0 = 0;
+        for (;; ++k) {
+            const int nt = (chi(k) - clo(k) + cw - 1) / cw;
+            if (t < t0 + nt) break;
+            t0 += nt;
         }
-        double s[4] = { 0.0, 0.0, 0.0, 0.0 };
-        double t[4] = { 0.0, 0.0, 0.0, 0.0 };
-        for (int k = 2 * lane; k < lmax; k += 128) {
-            double2 a0[4], a1[4];
+        const int c0 = clo(k) + (t - t0) * cw, c1 = min(chi(k), c0 + cw);
+        const int row = (k << 6) + 2 * lane;
+        double2 acc[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                a0[u] = (k < ln[u]) ? gt_ld2<NC>(m[u] + k) : make_double2(0.0, 0.0);
-                a1[u] = (k + 64 < ln[u]) ? gt_ld2<NC>(m[u] + k + 64) : make_double2(0.0, 0.0);
-            }
+        for (int u = 0; u < 4; ++u) acc[u] = make_double2(0.0, 0.0);
+        if (row < ld) {
+            const double* mp = M + row + size_t(c0) * ld;
+            int j = c0;
+            for (; j + 7 < c1; j += 8, mp += 8 * size_t(ld)) {
+                double2 a[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (k < ln[u]) {
-                    const double2 x = *reinterpret_cast<const double2*>(v[u] + k);
-                    if (k >= sk[u]) s[u] = fma(a0[u].x, x.x, s[u]);
-                    if (k + 1 < ln[u]) s[u] = fma(a0[u].y, x.y, s[u]);
+                for (int u = 0; u < 8; ++u) a[u] = __ldg(reinterpret_cast<const double2*>(mp + u * size_t(ld)));
+#pragma unroll
+                for (int u = 0; u < 8; u += 2) {
+                    const double2 x = *reinterpret_cast<const double2*>(vec + j + u);
+                    acc[u >> 1].x = fma(a[u].x, x.x, acc[u >> 1].x);
+                    acc[u >> 1].y = fma(a[u].y, x.x, acc[u >> 1].y);
+                    acc[u >> 1].x = fma(a[u + 1].x, x.y, acc[u >> 1].x);
+                    acc[u >> 1].y = fma(a[u + 1].y, x.y, acc[u >> 1].y);
                 }
-                if (k + 64 < ln[u]) {
-                    const double2 x = *reinterpret_cast<const double2*>(v[u] + k + 64);
-                    t[u] = fma(a1[u].x, x.x, t[u]);
-                    if (k + 65 < ln[u]) t[u] = fma(a1[u].y, x.y, t[u]);
-                }
+            }
+            for (; j < c1; ++j, mp += ld) {
+                const double2 a = __ldg(reinterpret_cast<const double2*>(mp));
+                const double x = vec[j];
+                acc[0].x = fma(a.x, x, acc[0].x);
+                acc[0].y = fma(a.y, x, acc[0].y);
             }
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            double q = s[u] + t[u];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-            if (lane == 0 && c + u < c_hi) out[c + u] = q;
-        }
+        double2 r_;
+        r_.x = (acc[0].x + acc[1].x) + (acc[2].x + acc[3].x);
+        r_.y = (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y);
+        *reinterpret_cast<double2*>(part + (size_t(t) << 6) + 2 * lane) = r_;
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+        const int k = r >> 6;
+        int t0 = 0;
+        for (int kk = 0; kk < k; ++kk) t0 += (chi(kk) - clo(kk) + cw - 1) / cw;
+        const int nt = (chi(k) - clo(k) + cw - 1) / cw;
+        double sum = 0.0;
+        for (int q = 0; q < nt; ++q) sum += part[(size_t(t0 + q) << 6) + (r & 63)];
+        out[r] = sum;
     }
 }
 
-// d[j] = sum_{i <= j, i < supp} Jt[i, j] a[i]
-__device__ __forceinline__ void gt_jt_dots(const double* __restrict__ Jt, int n, int ld, int supp, const double* __restrict__ a,
-    double* __restrict__ d)
-{
-    gt_seg_dots<true>(Jt, 0, n, [&](int j) { return size_t(j) * ld; }, [&](int j) { return min(j + 1, supp); }, [](int) { return 0; },
-        [](int) { return 0; }, a, d);
-}
-// z[i] = sum_{j >= i} Jt[i, j] v[j]   (JtT[j + i ld] = Jt[i, j]); odd rows start one element early (skipped in the sum)
-__device__ __forceinline__ void gt_j_dots(const double* __restrict__ JtT, int n, int ld, const double* __restrict__ v, double* __restrict__ z)
-{
-    gt_seg_dots<true>(JtT, 0, n, [&](int i) { return size_t(i) * ld + (i & ~1); }, [&](int i) { return n - (i & ~1); },
-        [](int i) { return i & ~1; }, [](int i) { return i & 1; }, v, z);
-}
-// out[c] = Q1[:, c] . vec for c in [0, nact): head columns from shared memory, the rest from the global workspace
+// out[c] = Q1[:, c] . vec for c in [0, nact): an 8-lane group per column (128-bit loads, three shuffles per column), head
+// columns from shared memory, the rest from the global workspace
 __device__ __forceinline__ void gt_q1_col_dots(const GtWork& W, int n, int ld, int q1s, int nact, const double* __restrict__ vec,
     double* __restrict__ out)
 {
-    const int ns = min(nact, q1s);
-    if (ns > 0)
-        gt_seg_dots<false>(W.Q1s, 0, ns, [&](int c) { return size_t(c) * ld; }, [&](int) { return n; }, [](int) { return 0; },
-            [](int) { return 0; }, vec, out);
-    if (nact > q1s)
-        gt_seg_dots<false>(W.Q1, q1s, nact, [&](int c) { return size_t(c) * ld; }, [&](int) { return n; }, [](int) { return 0; },
-            [](int) { return 0; }, vec, out);
+    const int lane = lane_id(), wp = warp_id(), nw = blockDim.x >> 5;
+    const int g8 = lane >> 3, l8 = lane & 7;
+    (void)n;
+    for (int cb = 4 * wp; cb < nact; cb += 4 * nw) {
+        const int c = cb + g8;
+        const bool on = c < nact;
+        const double* col = (c < q1s ? W.Q1s : W.Q1) + size_t(on ? c : 0) * ld;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        if (on) {
+            int k = 2 * l8;
+            for (; k + 48 < ld; k += 64) {
+                const double2 a0 = *reinterpret_cast<const double2*>(col + k), a1 = *reinterpret_cast<const double2*>(col + k + 16);
+                const double2 a2 = *reinterpret_cast<const double2*>(col + k + 32), a3 = *reinterpret_cast<const double2*>(col + k + 48);
+                const double2 x0 = *reinterpret_cast<const double2*>(vec + k), x1 = *reinterpret_cast<const double2*>(vec + k + 16);
+                const double2 x2 = *reinterpret_cast<const double2*>(vec + k + 32), x3 = *reinterpret_cast<const double2*>(vec + k + 48);
+                s0 = fma(a0.y, x0.y, fma(a0.x, x0.x, s0));
+                s1 = fma(a1.y, x1.y, fma(a1.x, x1.x, s1));
+                s2 = fma(a2.y, x2.y, fma(a2.x, x2.x, s2));
+                s3 = fma(a3.y, x3.y, fma(a3.x, x3.x, s3));
+            }
+            for (; k < ld; k += 16) {
+                const double2 a0 = *reinterpret_cast<const double2*>(col + k);
+                const double2 x0 = *reinterpret_cast<const double2*>(vec + k);
+                s0 = fma(a0.y, x0.y, fma(a0.x, x0.x, s0));
+            }
+        }
+        double q = (s0 + s1) + (s2 + s3);
+        q += __shfl_xor_sync(0xffffffffu, q, 4);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+        if (on && l8 == 0) out[c] = q;
+    }
 }
 
 // out[r] = sum_{c < nact} Q1[r, c] * vec[c]: a thread owns a PAIR of rows (one 128-bit load per column), the column range
@@ -478,7 +502,7 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
 
     if (fail == 0) {
         // ---- unconstrained minimiser x = Jt Jt' (-c) -------------------------------------------------------------------------
-        gt_jt_dots(Jt, n, ld, n, W.av, W.d);
+        gt_trap_mv<false>(JtT, ld, n, n, W.av, W.d, W.part);
         // ---- norms of the general rows (the reference's summation order: columns ascending) ---------------------------------
         for (int i = tid; i < mg; i += T) {
             double s = 0.0;
@@ -500,7 +524,7 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
             W.norm[i] = sqrt(s);
         }
         __syncthreads();
-        gt_j_dots(JtT, n, ld, W.d, W.x);
+        gt_trap_mv<true>(Jt, ld, n, n, W.d, W.x, W.part);
         __syncthreads();
         GT_T(0);
 
@@ -569,7 +593,7 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
                     for (int k = tid; k < n; k += T) W.av[k] = sg * gAin[(nvl - meq) + size_t(k) * m];
                 }
                 __syncthreads();
-                gt_jt_dots(Jt, n, ld, supp, W.av, W.d);
+                gt_trap_mv<false>(JtT, ld, n, supp, W.av, W.d, W.part);
             } else {
                 const int j = nvl - mg;
                 if (j < n) { bj = j; bsign = -1.0; }
@@ -613,7 +637,8 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
                 }
                 GT_T(4);
                 // z = Jt zt ; r = S d1
-                gt_j_dots(JtT, n, ld, W.zt, W.z);
+                gt_trap_mv<true>(Jt, ld, n, n, W.zt, W.z, W.part);
+                __syncthreads();
                 if (nact > 0) gt_row_dots(S, ldn, nact, 0, nact, [&](int r_) { return size_t(W.rowmap[r_]); }, W.d1, W.r, W.part);
                 __syncthreads();
                 GT_T(5);
