@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libcopra_b200.so")
 
 HOST, DEVICE = 0, 1
 FLAG_NO_REG = 1  # COPRA_B200_FLAG_NO_REG: no 1e-6 I regulariser (single cost evaluation)
+FLAG_STABLE_BOUND_PATTERN = 2  # device inputs: the +-inf pattern of trajectory bounds is unchanged since the last build
 COST_KINDS = {"trajectory": 0, "target": 1, "control": 2, "mixed": 3}
 CSTR_KINDS = {"trajectory": 0, "control": 1, "mixed": 2, "trajectory_bound": 3, "control_bound": 4}
 GET = dict(Phi=0, Psi=1, xi=2, Q=3, c=4, Aeq=5, beq=6, Aineq=7, bineq=8, lb=9, ub=10)
@@ -66,7 +67,10 @@ EXPORTS = ["copra_b200_abi_version", "copra_b200_device_count", "copra_b200_crea
            "copra_b200_last_error", "copra_b200_set_stream", "copra_b200_synchronize", "copra_b200_launch_count",
            "copra_b200_last_timing", "copra_b200_condense", "copra_b200_solve_qp_batch", "copra_b200_lmpc_sizes",
            "copra_b200_lmpc_run", "copra_b200_lmpc_build", "copra_b200_lmpc_solve", "copra_b200_lmpc_download",
-           "copra_b200_lmpc_results", "copra_b200_dgemm_batch", "copra_b200_lmpc_resolve", "copra_b200_fp64_peaks"]
+           "copra_b200_lmpc_results", "copra_b200_dgemm_batch", "copra_b200_lmpc_resolve", "copra_b200_fp64_peaks",
+           "copra_b200_lmpc_built_sizes", "copra_b200_last_solver", "copra_b200_hessian_is_shared", "copra_b200_multi_create", "copra_b200_multi_destroy",
+           "copra_b200_multi_last_error", "copra_b200_multi_size", "copra_b200_multi_shard", "copra_b200_multi_timing",
+           "copra_b200_multi_launch_count", "copra_b200_multi_lmpc_run", "copra_b200_multi_lmpc_resolve"]
 
 _lib = None
 
@@ -110,6 +114,22 @@ def load():
         lib.copra_b200_dgemm_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int,
                                                C.c_longlong, C.c_void_p, C.c_int, C.c_longlong, C.c_double, C.c_void_p, C.c_int,
                                                C.c_longlong, C.c_int, C.c_int]
+        lib.copra_b200_lmpc_built_sizes.argtypes = [C.c_void_p, C.POINTER(Sizes)]
+        lib.copra_b200_last_solver.argtypes = [C.c_void_p]
+        lib.copra_b200_last_solver.restype = C.c_char_p
+        lib.copra_b200_hessian_is_shared.argtypes = [C.c_void_p]
+        lib.copra_b200_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+        lib.copra_b200_multi_destroy.argtypes = [C.c_void_p]
+        lib.copra_b200_multi_destroy.restype = None
+        lib.copra_b200_multi_last_error.argtypes = [C.c_void_p]
+        lib.copra_b200_multi_last_error.restype = C.c_char_p
+        lib.copra_b200_multi_size.argtypes = [C.c_void_p]
+        lib.copra_b200_multi_shard.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _ip]
+        lib.copra_b200_multi_timing.argtypes = [C.c_void_p, C.c_int, C.POINTER(Timing), C.POINTER(C.c_double)]
+        lib.copra_b200_multi_launch_count.argtypes = [C.c_void_p]
+        lib.copra_b200_multi_launch_count.restype = C.c_longlong
+        lib.copra_b200_multi_lmpc_run.argtypes = [C.c_void_p, C.POINTER(Problem), C.POINTER(Results)]
+        lib.copra_b200_multi_lmpc_resolve.argtypes = [C.c_void_p, Array, C.POINTER(Results)]
         _lib = lib
     return _lib
 
@@ -347,6 +367,12 @@ class Engine:
         out["sizes"] = s
         return {k: v for k, v in out.items() if k in want or k == "sizes"}
 
+    def last_solver(self):
+        return self.lib.copra_b200_last_solver(self.h).decode()
+
+    def hessian_is_shared(self):
+        return bool(self.lib.copra_b200_hessian_is_shared(self.h))
+
     def fp64_peaks(self):
         """measured (DFMA, DMMA) TFLOP/s of this device"""
         a, b = C.c_double(0), C.c_double(0)
@@ -387,3 +413,87 @@ class Engine:
         if buf.size:
             self._check(self.lib.copra_b200_lmpc_download(self.h, GET[what], buf.ctypes.data, HOST))
         return np.swapaxes(buf, 1, 2) if len(shp) == 2 else buf
+
+
+class MultiEngine:
+    """Data-parallel sharder (copra_b200_multi_*): one engine handle + host thread per listed device, the batch split
+    into contiguous instance ranges, results gathered by DMA into the caller's buffers."""
+
+    def __init__(self, devices=None):
+        self.lib = load()
+        self.m = C.c_void_p()
+        if devices is None:
+            rc = self.lib.copra_b200_multi_create(None, 0, C.byref(self.m))
+        else:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self.lib.copra_b200_multi_create(arr, len(devices), C.byref(self.m))
+        if rc != 0:
+            raise CopraB200Error(rc, "copra_b200_multi_create failed (no usable sm_100 CUDA device? there is no CPU fallback)")
+
+    def close(self):
+        if getattr(self, "m", None):
+            self.lib.copra_b200_multi_destroy(self.m)
+            self.m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise CopraB200Error(rc, self.lib.copra_b200_multi_last_error(self.m).decode())
+
+    def size(self):
+        return int(self.lib.copra_b200_multi_size(self.m))
+
+    def launch_count(self):
+        return int(self.lib.copra_b200_multi_launch_count(self.m))
+
+    def shards(self):
+        out = []
+        for g in range(self.size()):
+            d, lo, hi = C.c_int(0), C.c_int(0), C.c_int(0)
+            self._check(self.lib.copra_b200_multi_shard(self.m, g, C.byref(d), C.byref(lo), C.byref(hi)))
+            out.append((d.value, lo.value, hi.value))
+        return out
+
+    def timing(self, g):
+        t, w = Timing(), C.c_double(0)
+        self._check(self.lib.copra_b200_multi_timing(self.m, g, C.byref(t), C.byref(w)))
+        d = {k: getattr(t, k) for k, _ in Timing._fields_}
+        d["wall_ms"] = w.value
+        return d
+
+    @staticmethod
+    def _outputs(B, s):
+        return dict(control=np.zeros((B, s["nU"])), trajectory=np.zeros((B, s["X"])), x=np.zeros((B, s["nvar"])),
+                    status=np.full(B, -1, np.int32), iters=np.zeros((B, 2), np.int32), nact=np.zeros(B, np.int32),
+                    iact=np.zeros((B, s["nvar"]), np.int32))
+
+    def lmpc_run(self, bp_or_hb, sizes, results=None):
+        """`sizes` from Engine.sizes(); `results` an optional prepared ctypes Results (e.g. pinned torch buffers)."""
+        hb = bp_or_hb if isinstance(bp_or_hb, HostBatch) else HostBatch(bp_or_hb)
+        if results is not None:
+            self._check(self.lib.copra_b200_multi_lmpc_run(self.m, C.byref(hb.problem), C.byref(results)))
+            return None
+        out = self._outputs(hb.problem.batch, sizes)
+        r = Results()
+        r.memory = HOST
+        for k, v in out.items():
+            setattr(r, k, v.ctypes.data)
+        self._check(self.lib.copra_b200_multi_lmpc_run(self.m, C.byref(hb.problem), C.byref(r)))
+        return out
+
+    def lmpc_resolve(self, x0, sizes):
+        x0 = np.ascontiguousarray(np.asarray(x0, dtype=np.float64))
+        out = self._outputs(x0.shape[0], sizes)
+        r = Results()
+        r.memory = HOST
+        for k, v in out.items():
+            setattr(r, k, v.ctypes.data)
+        a = Array()
+        a.ptr, a.stride = x0.ctypes.data, x0.shape[1]
+        self._check(self.lib.copra_b200_multi_lmpc_resolve(self.m, a, C.byref(r)))
+        return out

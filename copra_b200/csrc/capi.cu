@@ -8,6 +8,7 @@
 #include "launch.h"
 #include "gi_solver.cuh"
 #include "gi_thin.cuh"
+#include "slice.h"
 
 #include <cfloat>
 #include <cmath>
@@ -60,6 +61,7 @@ struct copra_b200_handle {
     bool factor_valid = false; // the thin solver's R^-1 of the last build is resident (re-solves skip the factorisation)
     bool rows_filled = false;  // Aeq / Aineq of the last build are materialised (the structured solver never reads them)
     bool use_thin = false;     // the last build is solved by the thin kernel (gi_thin.cuh)
+    const char* solver = "";   // K5+K6 kernel(s) of the last solve
     GtBatch gt{};
     GtPlan gtplan{};
     BuildParams bp{};
@@ -328,7 +330,11 @@ int make_plan(copra_b200_handle* h, const copra_b200_problem* p, Plan& pl)
             std::vector<int> ll, ul;
             copra_b200_handle::TbKey key{ c.lower.ptr, c.upper.ptr, brows };
             auto hit = h->tb_cache.find(key);
-            if (p->memory == COPRA_B200_DEVICE && hit != h->tb_cache.end()) {
+            // DEVICE inputs: the +-inf pattern is read back from instance 0 on EVERY build (one small D2H + sync) unless the
+            // caller vouches with COPRA_B200_FLAG_STABLE_BOUND_PATTERN that it has not changed since the last build that
+            // used these pointers (a rewritten or re-allocated bound tensor would otherwise reuse stale line lists)
+            const bool may_cache = p->memory == COPRA_B200_DEVICE && (p->flags & COPRA_B200_FLAG_STABLE_BOUND_PATTERN);
+            if (may_cache && hit != h->tb_cache.end()) {
                 ll = hit->second.first;
                 ul = hit->second.second;
             } else {
@@ -346,7 +352,10 @@ int make_plan(copra_b200_handle* h, const copra_b200_problem* p, Plan& pl)
                             if ((a != -INFINITY) != (lo[l] != -INFINITY) || (u != INFINITY) != (up[l] != INFINITY))
                                 return fail(h, COPRA_B200_E_ARG, "constraint %d: the set of infinite trajectory bounds must be the same for every instance", i);
                         }
-                } else h->tb_cache[key] = std::make_pair(ll, ul);
+                } else if (may_cache) {
+                    if (h->tb_cache.size() > 64) h->tb_cache.clear();
+                    h->tb_cache[key] = std::make_pair(ll, ul);
+                }
             }
             if (!ll.empty()) push(0, N + 1, 1, 0, false, 1, ll);
             if (!ul.empty()) push(0, N + 1, 1, 0, false, 2, ul);
@@ -391,9 +400,11 @@ int run_gi(copra_b200_handle* h, GiBatch& G)
     G.max_iter = 50 * (G.meq + G.m + 2 * G.n) + 100;
     G.j_smem = plan.j_smem; G.s_smem = plan.s_smem; G.a_smem = plan.a_smem;
     G.ws = nullptr; G.ws_stride = plan.ws_stride;
+    h->solver = plan.small ? "gi_small_kernel" : "gi_batch_kernel";
     if (plan.cluster > 0) {
         int nclusters = gi_cluster_max_clusters(plan);
         if (nclusters > 0) {
+            h->solver = "gi_cluster_kernel";
             nclusters = std::min(nclusters, G.batch);
             const size_t n = G.n;
             double* Sws = nullptr;
@@ -497,6 +508,7 @@ int run_gt(copra_b200_handle* h, double* x, int* status, int* iters, int* nact, 
     T.counter = counter;
     T.vsmall = h->vsmall;
     T.max_iter = 50 * (P.meq + P.mineq + 2 * P.nvar) + 100;
+    h->solver = "gt_factor_kernel + gi_thin_kernel";
     cudaError_t e = gt_launch(T, plan, h->stream);
     if (e != cudaSuccess) return fail(h, COPRA_B200_E_CUDA, "gt_launch: %s", cudaGetErrorString(e));
     h->launches += 1; h->call_launches += 1;
@@ -838,6 +850,7 @@ int copra_b200_set_stream(copra_b200_handle* h, void* s)
     CU(cudaStreamSynchronize(h->stream));
     if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
     h->stream = static_cast<cudaStream_t>(s);
+    h->tb_cache.clear();
     return 0;
 }
 
@@ -919,6 +932,17 @@ int copra_b200_lmpc_sizes(copra_b200_handle* h, const copra_b200_problem* p, cop
     return 0;
 }
 
+const char* copra_b200_last_solver(const copra_b200_handle* h) { return h ? h->solver : ""; }
+int copra_b200_hessian_is_shared(const copra_b200_handle* h) { return (h && h->built && h->bp.sQ == 0) ? 1 : 0; }
+
+int copra_b200_lmpc_built_sizes(copra_b200_handle* h, copra_b200_sizes* s)
+{
+    if (!h || !s) return COPRA_B200_E_ARG;
+    if (!h->built) return fail(h, COPRA_B200_E_STATE, "no build is resident on this handle");
+    s->X = h->sz.X; s->nU = h->sz.nU; s->nvar = h->sz.nvar; s->meq = h->sz.meq; s->mineq = h->sz.mineq; s->q = h->sz.q;
+    return 0;
+}
+
 int copra_b200_lmpc_build(copra_b200_handle* h, const copra_b200_problem* p)
 {
     if (!h) return COPRA_B200_E_ARG;
@@ -948,31 +972,13 @@ int copra_b200_lmpc_run(copra_b200_handle* h, const copra_b200_problem* p, const
     copra_b200_sizes sz;
     int rc = copra_b200_lmpc_sizes(h, p, &sz);
     if (rc) return rc;
-    auto adv = [](copra_b200_array a, long long b0) { if (a.ptr && a.stride) a.ptr += b0 * a.stride; return a; };
     long long total_launches = 0;
     for (long long b0 = 0; b0 < p->batch; b0 += kChunk) {
-        copra_b200_problem q = *p;
-        q.batch = int(std::min<long long>(kChunk, p->batch - b0));
-        q.A = adv(p->A, b0); q.B = adv(p->B, b0); q.d = adv(p->d, b0); q.x0 = adv(p->x0, b0);
-        q.R = adv(p->R, b0); q.r = adv(p->r, b0); q.x0lb = adv(p->x0lb, b0); q.x0ub = adv(p->x0ub, b0);
-        std::vector<copra_b200_cost> costs(p->costs, p->costs + p->ncost);
-        std::vector<copra_b200_constraint> cstrs(p->cstrs, p->cstrs + p->ncstr);
-        for (auto& c : costs) { c.M = adv(c.M, b0); c.N = adv(c.N, b0); c.p = adv(c.p, b0); c.w = adv(c.w, b0); }
-        for (auto& c : cstrs) { c.E = adv(c.E, b0); c.G = adv(c.G, b0); c.f = adv(c.f, b0); c.lower = adv(c.lower, b0); c.upper = adv(c.upper, b0); }
-        q.costs = costs.data();
-        q.cstrs = cstrs.data();
+        ProblemSlice q;
+        slice_problem(*p, b0, int(std::min<long long>(kChunk, p->batch - b0)), q);
         copra_b200_results rr{};
-        if (r) {
-            rr = *r;
-            if (r->control) rr.control = r->control + b0 * sz.nU;
-            if (r->trajectory) rr.trajectory = r->trajectory + b0 * sz.X;
-            if (r->x) rr.x = r->x + b0 * sz.nvar;
-            if (r->status) rr.status = r->status + b0;
-            if (r->iters) rr.iters = r->iters + 2 * b0;
-            if (r->nact) rr.nact = r->nact + b0;
-            if (r->iact) rr.iact = r->iact + b0 * sz.nvar;
-        }
-        if ((rc = do_build(h, &q))) return rc;
+        if (r) rr = slice_results(*r, b0, sz);
+        if ((rc = do_build(h, &q.p))) return rc;
         if ((rc = do_solve(h, r ? &rr : nullptr))) return rc;
         total_launches += h->call_launches;
     }

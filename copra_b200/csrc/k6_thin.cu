@@ -86,7 +86,7 @@ GtPlan gt_plan(const GtShape& sh, int batch, int sms, size_t smem_optin)
     p.ok = base + 2048 <= smem_optin;
     if (!p.ok) return p;
     // one CTA per SM; whatever shared memory the vectors and tables leave holds the head columns of Q1
-    int per_sm = std::max(1, gt_env_int("COPRA_B200_THIN_CTAS_PER_SM", 1));
+    int per_sm = std::max(1, gt_env_int("COPRA_B200_THIN_CTAS_PER_SM", 2));
     per_sm = std::min(per_sm, 2048 / p.threads);
     per_sm = std::min<int>(per_sm, int((smem_optin + 1024) / (base + 1024)));
     const size_t budget = (smem_optin + 1024) / per_sm - 1024 - 1024; // per CTA, minus static shared memory headroom

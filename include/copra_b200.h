@@ -106,6 +106,11 @@ typedef struct {
 /* LMPC::updateSystem starts every Hessian at 1e-6*I (src/LMPC.cpp:228-229).  The facade sets NO_REG when it
  * evaluates ONE cost function in isolation (CostFunction::Q() getter), where the reference has no such term. */
 #define COPRA_B200_FLAG_NO_REG 1
+/* DEVICE inputs only: the caller guarantees that the +-inf pattern of every TrajectoryBoundConstraint's lower / upper
+ * (which decides the number of inequality rows, include/constraints.h:247-254) is unchanged since the previous build
+ * on this handle that used the same pointers, so the engine may skip reading it back.  Without the flag the pattern is
+ * re-read from instance 0 on every build. */
+#define COPRA_B200_FLAG_STABLE_BOUND_PATTERN 2
 
 typedef struct {
     int X;      /* nx*(N+1) */
@@ -205,6 +210,34 @@ int copra_b200_lmpc_results(copra_b200_handle* h, const double* x, double* contr
 /* assembled stage of the last build, reference layout (LMPC::Q() c() Aeq() ... getters,
  * include/LMPC.h:105-127); `out` must hold batch * size doubles. */
 int copra_b200_lmpc_download(copra_b200_handle* h, int what, double* out, int memory);
+
+/* introspection for benchmarks / logs: the K5+K6 kernel(s) the last solve ran ("gi_small_kernel", "gi_cluster_kernel",
+ * "gi_batch_kernel", "gt_factor_kernel + gi_thin_kernel") and whether the resident build found the Hessian batch-invariant
+ * (A, B and every cost's M, N, w shared: assembled and factored once) */
+const char* copra_b200_last_solver(const copra_b200_handle* h);
+int copra_b200_hessian_is_shared(const copra_b200_handle* h);
+/* sizes of the build resident on the handle (E_STATE without one) */
+int copra_b200_lmpc_built_sizes(copra_b200_handle* h, copra_b200_sizes* s);
+
+/* ---- data-parallel sharder ------------------------------------------------------------------------------
+ * The batch of independent controllers is split by instance index into contiguous ranges
+ * [g*ceil(B/G), (g+1)*ceil(B/G)), one per device; every device has its own engine handle driven by its own host thread,
+ * parameters are uploaded per shard and every shard's results are written by DMA into the caller's result buffers (page-lock
+ * them for direct DMA).  No collective on the path; results are bit-identical to a single-device run.  HOST arrays only.
+ * `devices` NULL / ndev <= 0 = every visible device; a device may be listed more than once (several handles share it). */
+typedef struct copra_b200_multi copra_b200_multi;
+int copra_b200_multi_create(const int* devices, int ndev, copra_b200_multi** out);
+void copra_b200_multi_destroy(copra_b200_multi* m);
+const char* copra_b200_multi_last_error(const copra_b200_multi* m);
+int copra_b200_multi_size(const copra_b200_multi* m);
+/* device ordinal and instance range [lo, hi) of shard g in the last run */
+int copra_b200_multi_shard(const copra_b200_multi* m, int g, int* device, int* lo, int* hi);
+/* stage timings of shard g's last call and the host wall time of the whole sharded call */
+int copra_b200_multi_timing(const copra_b200_multi* m, int g, copra_b200_timing* t, double* wall_ms);
+long long copra_b200_multi_launch_count(const copra_b200_multi* m);
+/* LMPC::solve for the whole batch (see copra_b200_lmpc_run) / receding-horizon re-solve (see copra_b200_lmpc_resolve) */
+int copra_b200_multi_lmpc_run(copra_b200_multi* m, const copra_b200_problem* p, const copra_b200_results* r);
+int copra_b200_multi_lmpc_resolve(copra_b200_multi* m, copra_b200_array x0, const copra_b200_results* r);
 
 #ifdef __cplusplus
 }

@@ -287,7 +287,9 @@ def lmpc_batch(probs, threads=None):
 
 
 def hw_threads():
+    """host threads this process may use: the scheduler affinity mask, not the machine's core count"""
+    import os
     try:
-        return len(os.sched_getaffinity(0))
+        return max(1, len(os.sched_getaffinity(0)))
     except AttributeError:
-        return lib().orc_hw_threads()
+        return max(1, lib().orc_hw_threads())
