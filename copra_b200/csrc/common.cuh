@@ -52,6 +52,20 @@ __device__ __forceinline__ MinIdx warp_argmin(MinIdx m)
     return r;
 }
 
+// Slack of bound row j in [0, 2n): upper rows first (-x_v >= -ub_v), then lower rows (x_v >= lb_v); `active` is indexed
+// by constraint (general rows first, then the 2n bound rows).  A variable PINNED by lb == ub whose one bound is already
+// active satisfies the other by definition: its slack is 0, not the rounding residue of x_v.  (A residue of -1e-16 would
+// make the solver try to add the negated normal of an active row and report a spurious "infeasible"; this is the default
+// state of InitialStateLMPC, whose x0 bounds are both ps->x0 until resetInitialStateBounds -- src/InitialStateLMPC.cpp:24-25.)
+__device__ __forceinline__ double gi_bound_slack(int j, int n, int mg, const double* x, const double* lb, const double* ub,
+    const unsigned char* active)
+{
+    const int v = j < n ? j : j - n;
+    const double s = (j < n) ? ub[v] - x[v] : x[v] - lb[v];
+    const int twin = mg + (j < n ? j + n : j - n);
+    return (active[twin] && lb[v] == ub[v]) ? 0.0 : s;
+}
+
 // Block-wide reductions through a small smem scratch (>= kMaxWarps entries each).  All threads
 // must call; result is returned to every thread.  Ends with a __syncthreads so scratch is reusable.
 __device__ __forceinline__ double block_sum(double v, double* scratch)

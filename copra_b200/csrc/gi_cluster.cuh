@@ -409,7 +409,7 @@ __device__ inline int gc_solve(const GiView& P, const GcLayout& L, GcWork& W, do
             __syncthreads();
         }
         for (int j = b0 + tid; j < b1; j += T) // bound rows: upper (-x_j >= -ub_j) then lower (x_j >= lb_j)
-            consider(mg + j, (j < n) ? W.ub[j] - W.x[j] : W.x[j - n] - W.lb[j - n], 1.0);
+            consider(mg + j, gi_bound_slack(j, n, mg, W.x, W.lb, W.ub, W.active), 1.0);
         {
             const MinIdx mine = block_argmin(best, W.red, W.redi);
             if (best.i == mine.i && mine.i >= 0) { scal[0] = best_s; scal[1] = (mine.i < meq) ? double(W.sgn[mine.i]) : -1.0; }

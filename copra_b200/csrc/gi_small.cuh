@@ -440,8 +440,7 @@ __device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, do
                 }
             }
             for (int j = tid; j < 2 * n; j += kSmT) { // bound rows: upper (-x_j >= -ub_j) then lower (x_j >= lb_j)
-                const double s = (j < n) ? W.ub[j] - W.x[j] : W.x[j - n] - W.lb[j - n];
-                consider(mg + j, s);
+                consider(mg + j, gi_bound_slack(j, n, mg, W.x, W.lb, W.ub, W.active));
             }
             {
                 const MinIdx wm = warp_argmin(best);

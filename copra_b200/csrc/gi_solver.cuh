@@ -383,8 +383,7 @@ __device__ inline int gi_solve(const GiView& P, GiWork& W, const GiOut& O, doubl
                 double s;
                 if (i < meq) s = double(W.sgn[i]) * (W.sl[i] - P.beq[i]);
                 else if (i < mg) s = P.bineq[i - meq] - W.sl[i];
-                else if (i < mg + n) s = W.ub[i - mg] - W.x[i - mg];
-                else s = W.x[i - mg - n] - W.lb[i - mg - n];
+                else s = gi_bound_slack(i - mg, n, mg, W.x, W.lb, W.ub, W.active);
                 if (fabs(s) < vsmall) s = 0.0;
                 if (i < meq) {
                     if (s > 0.0) W.sgn[i] = -W.sgn[i];

@@ -549,8 +549,7 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
                 double s;
                 if (i < meq) s = double(W.sgn[i]) * (W.sl[i] - W.bv[i]);
                 else if (i < mg) s = W.bv[i] - W.sl[i];
-                else if (i < mg + n) s = W.ub[i - mg] - W.x[i - mg];
-                else s = W.x[i - mg - n] - W.lb[i - mg - n];
+                else s = gi_bound_slack(i - mg, n, mg, W.x, W.lb, W.ub, W.active);
                 if (fabs(s) < vsmall) s = 0.0;
                 if (i < meq) {
                     if (s > 0.0) W.sgn[i] = -W.sgn[i];

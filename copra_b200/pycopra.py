@@ -484,7 +484,9 @@ class InitialStateLMPC(LMPC):
         super().initialize_controller(ps)
         nx = ps.x_dim
         self._R, self._r = np.zeros((nx, nx)), np.zeros(nx)
-        self._x0lb, self._x0ub = np.full(nx, -np.inf), np.full(nx, np.inf)
+        # reference defaults (src/InitialStateLMPC.cpp:21-28): both bounds are ps->x0, i.e. x0 stays pinned until
+        # reset_initial_state_bounds is called (None = let the C ABI apply that default from the current x0)
+        self._x0lb = self._x0ub = None
 
     def reset_initial_state_cost(self, R, r):
         self._R = np.atleast_2d(np.asarray(R, dtype=np.float64)).copy()

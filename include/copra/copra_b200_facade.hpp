@@ -786,6 +786,7 @@ public:
     void useSolver(std::unique_ptr<SolverInterface>&& solver) { sol_ = std::move(solver); }
     virtual void initializeController(const std::shared_ptr<PreviewSystem>& ps)
     {
+        if (ps_) snapshotIfStale();
         ps_ = ps;
         clearConstraintMatrices();
     }
@@ -803,8 +804,9 @@ public:
         b200::check(copra_b200_lmpc_sizes(h, D.finish(), &sz));
         constraints_.nrEqConstr = sz.meq;
         constraints_.nrIneqConstr = sz.mineq;
-        control_.resize(sz.nU);
-        trajectory_.resize(sz.X);
+        // results go to temporaries and are committed only on success: the reference leaves control() / trajectory() at
+        // their previous values when the solver fails (updateResults is skipped, src/LMPC.cpp:95-97)
+        Eigen::VectorXd control(sz.nU), trajectory(sz.X);
         bool success = false;
         B200Solver* native = dynamic_cast<B200Solver*>(sol_.get());
         if (native) {
@@ -813,7 +815,7 @@ public:
             int status = -1, iters[2] = { 0, 0 }, nact = 0;
             std::vector<int> iact(size_t(sz.nvar), 0);
             copra_b200_results R{};
-            R.control = control_.data(); R.trajectory = trajectory_.data(); R.x = x.data(); R.status = &status; R.iters = iters;
+            R.control = control.data(); R.trajectory = trajectory.data(); R.x = x.data(); R.status = &status; R.iters = iters;
             R.nact = &nact; R.iact = iact.data(); R.memory = COPRA_B200_HOST;
             native->SI_problem(sz.nvar, sz.meq, sz.mineq);
             b200::check(copra_b200_lmpc_run(h, D.finish(), &R));
@@ -833,7 +835,11 @@ public:
             const auto t1 = clock::now();
             success = sol_->SI_solve(Q_, c_, Aeq_, beq_, Aineq_, bineq_, lb_, ub_);
             solveTime_ = std::chrono::duration<double>(clock::now() - t1).count();
-            if (success) b200::check(copra_b200_lmpc_results(h, sol_->SI_result().data(), control_.data(), trajectory_.data(), COPRA_B200_HOST));
+            if (success) b200::check(copra_b200_lmpc_results(h, sol_->SI_result().data(), control.data(), trajectory.data(), COPRA_B200_HOST));
+        }
+        if (success) {
+            control_ = control;
+            trajectory_ = trajectory;
         }
         lastSizes_ = sz;
         checkDeleteCostsAndConstraints();
@@ -847,11 +853,13 @@ public:
 
     void addCost(const std::shared_ptr<CostFunction>& costFun)
     {
+        snapshotIfStale();
         costFun->initializeCost(*ps_);
         spCost_.emplace_back(costFun);
     }
     void addConstraint(const std::shared_ptr<Constraint>& constr)
     {
+        snapshotIfStale();
         constr->initializeConstraint(*ps_);
         switch (constr->constraintType()) { // src/LMPC.cpp:173-197
         case ConstraintFlag::EqualityConstraint: constraints_.spEqConstr.emplace_back(std::static_pointer_cast<EqIneqConstraint>(constr)); break;
@@ -861,19 +869,22 @@ public:
         }
         constraints_.spConstr.emplace_back(constr);
     }
-    void clearCosts() noexcept { spCost_.clear(); }
+    void clearCosts() noexcept { snapshotIfStale(); spCost_.clear(); }
     void clearConstraints() noexcept
     {
+        snapshotIfStale();
         constraints_ = Constraints();
         clearConstraintMatrices();
     }
     void removeCost(const std::shared_ptr<CostFunction>& costFun)
     {
+        snapshotIfStale();
         auto it = std::find(spCost_.begin(), spCost_.end(), costFun);
         if (it != spCost_.end()) spCost_.erase(it);
     }
     void removeConstraint(const std::shared_ptr<Constraint>& constr)
     {
+        snapshotIfStale();
         auto drop = [&](auto& vec) {
             for (auto it = vec.begin(); it != vec.end(); ++it)
                 if (it->get() == constr.get()) { vec.erase(it); return; }
@@ -936,20 +947,35 @@ protected:
     }
     // The fused path leaves the assembled QP on the device; the getters pull it on demand.  If the
     // process-wide handle has built something else in the meantime, K1..K4 are re-run for this controller.
+    // The getters must return the QP that was SOLVED (the reference fills Q_, c_, ... inside solve()): every call that
+    // changes the description (add / remove / clear, the use_count purge, initializeController) first snapshots the
+    // matrices through snapshotIfStale(), so a rebuild here always describes the solved problem; its sizes are re-queried
+    // rather than trusted from the last solve.
     void refresh() const
     {
         if (!matricesStale_) return;
+        copra_b200_sizes sz = lastSizes_;
         if (myEpoch_ != b200::buildEpoch()) {
             b200::Description D;
             describe(D);
+            b200::check(copra_b200_lmpc_sizes(b200::handle(), D.finish(), &sz));
             b200::check(copra_b200_lmpc_build(b200::handle(), D.finish()));
             myEpoch_ = ++b200::buildEpoch();
         }
-        fetchMatrices(lastSizes_);
+        fetchMatrices(sz);
+    }
+    void snapshotIfStale() const noexcept
+    {
+        if (!matricesStale_) return;
+        try { refresh(); } catch (...) { matricesStale_ = false; }
     }
     // use_count based auto-removal, after the solve (src/LMPC.cpp:288-307, quirk Q3)
     void checkDeleteCostsAndConstraints()
     {
+        bool any = false;
+        for (auto& c : constraints_.spConstr) any = any || c.use_count() <= 2;
+        for (auto& c : spCost_) any = any || c.use_count() <= 1;
+        if (any) snapshotIfStale(); // the getters keep returning the QP that was just solved
         auto purge = [](auto& sp, long limit, bool warn) {
             for (auto it = sp.begin(); it != sp.end();) {
                 if (it->use_count() <= limit) {
@@ -1057,7 +1083,9 @@ public:
     // states change; condensing, Q and the constraint matrices stay resident on the device.  LMPC mode only.
     int resolve(copra_b200_array x0)
     {
-        if (myEpoch_ != b200::buildEpoch()) { // another controller used the process-wide engine since: full rebuild
+        if (myEpoch_ != b200::buildEpoch() || p_.batch > 65535 || p_.initial_state) {
+            // another controller used the process-wide engine since, the batch was processed in chunks (only the last chunk
+            // is resident), or x0 is a decision variable: full rebuild
             p_.x0 = x0;
             return solve();
         }

@@ -1,0 +1,137 @@
+"""GPU parity hardening: reference edge cases the first round never ran on the GPU -- finite lower
+trajectory bounds (quirk Q1), equalities at configuration size, +-inf / DBL_MAX bound mixes, the receding-horizon re-solve
+against the ORACLE, and batches of the C1 fixture through the thin solver (single input, odd supports)."""
+import numpy as np
+import pytest
+
+from copra_b200 import capi, workloads as wl
+from oracle import pyoracle as po
+from tests.test_gpu_parity import check_batch
+from tests.util import active_set, active_set_excused, x_err
+
+pytestmark = pytest.mark.gpu
+DBL_MAX = np.finfo(float).max
+
+
+def _c2_like(batch, N, T=0.03):
+    bp = wl.c2(batch=batch, N=N, T=T)
+    bp["name"] = "C2-N%d" % N
+    return bp
+
+
+@pytest.mark.parametrize("N", [50, 110])  # small kernel / thin kernel
+def test_finite_lower_trajectory_bound_quirk_q1(engine, N):
+    """src/constraints.cpp:289-296: a finite LOWER trajectory bound is stacked un-negated, i.e. it acts as x <= lower.
+    The engine follows the reference literally: stacked rows, right-hand sides and solutions equal the oracle's."""
+    bp = _c2_like(8, N, T=1.5 / N)
+    inf = np.inf
+    bp["constraints"][0] = dict(kind="trajectory_bound", lower=np.array([-inf, -3.0]), upper=np.array([inf, 0.0]))
+    w = check_batch(engine, bp)
+    out = engine.lmpc_run(bp)
+    assert (out["status"] == 0).all()
+    assert out["trajectory"][:, 1::2].max() <= -3.0 + 1e-6  # the "lower" bound really is an upper bound (quirk Q1)
+    # an instance whose x0 violates the un-negated row at step 0 (A = 0, b < 0) is infeasible in the reference too
+    bad = _c2_like(4, N, T=1.5 / N)
+    bad["constraints"][0] = dict(kind="trajectory_bound", lower=np.array([-inf, -7.0]), upper=np.array([inf, 0.0]))
+    out = engine.lmpc_run(bad)
+    for i in range(4):
+        assert out["status"][i] == po.lmpc(wl.instance(bad, i))["fail"] == 1
+    assert w.get("excused_rows", 0) == 0
+
+
+def _eq_system(batch, N=300, T=0.005, mass=5.0):
+    """reference fixture EqSystem (tests/systems.h:184-229, tests/TestLMPC.cpp EqSystem cases): hold the position with a
+    step-size equality TrajectoryConstraint E = [[1,0],[0,0]], f = x0 -> 2(N+1) equality rows, half of them 0 = 0"""
+    A, B, d = wl._double_integrator(T, mass)
+    rng = np.random.default_rng(11)
+    x0 = np.zeros((batch, 2))
+    x0[:, 0] = rng.uniform(-0.5, 0.5, batch) if batch > 1 else 0.0
+    E = np.zeros((2, 2))
+    E[0, 0] = 1.0
+    return dict(name="EqSystem-N%d" % N, nx=2, nu=1, N=N, batch=batch, initial_state=False, A=A, B=B, d=d, x0=x0,
+                costs=[dict(kind="target", M=np.eye(2), p=np.zeros(2), w=np.array([10.0, 10000.0])),
+                       dict(kind="control", N=np.eye(1), p=np.array([2.0]), w=np.array([1e-4]))],
+                constraints=[dict(kind="trajectory", E=E, f=x0.copy(), is_ineq=False)])
+
+
+@pytest.mark.parametrize("batch", [1, 20])  # cluster kernel / thin kernel
+def test_equalities_at_configuration_size(engine, batch):
+    """602 equality rows on 300 variables (n >= 300, meq > 0): the equality sign-flip rule and zero-normal rows at scale"""
+    bp = _eq_system(batch)
+    w = check_batch(engine, bp, instances=range(min(batch, 6)))
+    out = engine.lmpc_run(bp)
+    assert (out["status"] == 0).all()
+    pos = out["trajectory"][:, 0::2]
+    assert np.abs(pos - np.asarray(bp["x0"])[:, :1]).max() <= 1e-6  # the reference test's property: the system stays put
+    assert w.get("excused_rows", 0) == 0
+
+
+@pytest.mark.parametrize("N", [50, 120])
+def test_inf_and_dbl_max_bound_mixes(engine, N):
+    """quirk Q4: default bounds are -+DBL_MAX, user bounds may be +-inf; every mix must flow through K4..K6 without NaN and
+    keep QuadProg's row indices"""
+    bp = _c2_like(6, N, T=1.5 / N)
+    lower = np.array([[-np.inf], [-DBL_MAX], [-150.0], [-np.inf], [-DBL_MAX], [0.0]])
+    upper = np.array([[200.0], [np.inf], [DBL_MAX], [np.inf], [180.0], [220.0]])
+    bp["constraints"][1] = dict(kind="control_bound", lower=lower, upper=upper)
+    w = check_batch(engine, bp)
+    assert w.get("excused_rows", 0) == 0
+    bp["constraints"] = bp["constraints"][:1]  # no ControlBoundConstraint at all: the DBL_MAX defaults
+    check_batch(engine, bp)
+
+
+@pytest.mark.parametrize("make,shift", [(lambda: wl.c2(batch=48), np.array([0.0, 0.3])),
+                                        (lambda: wl.c3(batch=40), np.array([0.01, 0.02, 0.0, -0.01, 0.03, 0.0]))])
+def test_resolve_against_the_oracle(engine, make, shift):
+    """N1: copra_b200_lmpc_resolve with new x0 (cached condensing / Hessian / factor) against the ORACLE solving the
+    problem with that x0 from scratch -- not against another CUDA run"""
+    bp = make()
+    first = engine.lmpc_run(bp)
+    x0_new = np.array(bp["x0"]) + shift
+    again = engine.lmpc_resolve(x0_new, first["sizes"])
+    moved = dict(bp, x0=x0_new)
+    excused = 0
+    for i in range(0, bp["batch"], 3):
+        o = po.lmpc(wl.instance(moved, i))
+        assert again["status"][i] == o["fail"] == 0
+        assert x_err(again["x"][i], o["x"]) <= 1e-6 and x_err(again["control"][i], o["control"]) <= 1e-6
+        assert np.abs(again["trajectory"][i] - o["trajectory"]).max() <= 1e-6 * max(1.0, np.abs(o["trajectory"]).max())
+        excused += active_set_excused(active_set(again["iact"][i], again["nact"][i]), o)
+        assert int(again["iters"][i][0]) == o["iter"][0]
+    assert excused == 0
+    # a second re-solve back at the original x0 reproduces the first run bit for bit (nothing stale is cached)
+    back = engine.lmpc_resolve(np.array(bp["x0"]), first["sizes"])
+    assert np.array_equal(back["control"], first["control"]) and np.array_equal(back["iact"], first["iact"])
+
+
+def test_c1_fixture_batched_through_the_thin_solver(engine, monkeypatch):
+    """the BoundedSystem fixture (n = 300, single input: odd Toeplitz supports, 112 active trajectory-bound rows, cond(Q) ~ 3e4)
+    as a batch with perturbed x0 -> thin solver with a shared factor; and the same instances with the factor forced
+    per-instance (COPRA_B200_NO_SHARED_HESSIAN) must give identical results"""
+    base = wl.c1("target")
+    rng = np.random.default_rng(5)
+    B = 24
+    x0 = np.tile(np.asarray(base["x0"], float), (B, 1))
+    x0[1:, 1] += rng.uniform(-0.5, 0.5, B - 1)
+    bp = dict(base, batch=B, x0=x0, name="C1x24")
+    w = check_batch(engine, bp, instances=range(0, B, 4))
+    assert w["iter_diff"] == 0
+    shared = engine.lmpc_run(bp)
+    assert engine.hessian_is_shared() and "gi_thin_kernel" in engine.last_solver()
+    monkeypatch.setenv("COPRA_B200_NO_SHARED_HESSIAN", "1")
+    own = engine.lmpc_run(bp)
+    assert not engine.hessian_is_shared()
+    assert np.array_equal(shared["iact"], own["iact"]) and np.abs(shared["x"] - own["x"]).max() <= 1e-9
+
+
+def test_download_after_thin_solve_materialises_rows(engine):
+    """the thin solver never reads Aineq; the getter still returns the reference's stacked matrix (filled on demand)"""
+    bp = wl.c3(batch=20)
+    hb = capi.HostBatch(bp)
+    engine.lmpc_run(hb)
+    assert "gi_thin_kernel" in engine.last_solver()
+    A = engine.download(hb, "Aineq")
+    Q = engine.download(hb, "Q")
+    for i in (0, 19):
+        o = po.lmpc(wl.instance(bp, i), solve=False)
+        assert np.array_equal(A[i], o["Aineq"]) and np.array_equal(Q[i], o["Q"])

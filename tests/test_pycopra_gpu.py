@@ -229,3 +229,19 @@ def test_single_entry_getters_and_initial_state(copra):
     isl.reset_initial_state_bounds(Fx.x0 - 0.1, Fx.x0 + 0.1)
     assert isl.solve()
     assert np.all(np.abs(isl.initial_state() - Fx.x0) <= 0.1 + 1e-9)
+
+
+def test_initial_state_default_bounds_pin_x0(copra):
+    """reference constructor (src/InitialStateLMPC.cpp:21-28): x0lb = x0ub = ps->x0 until resetInitialStateBounds is called,
+    so with only an initial-state cost the optimal x0 is the given one"""
+    ps, _, _, _ = _controller(copra)
+    isl = copra.InitialStateLMPC(ps)
+    a, b = copra.TargetCost(Fx.M, -Fx.xd), copra.ControlCost(Fx.Nm, -Fx.ud)
+    a.weights(np.array([10.0, 100.0]))
+    b.weights(np.array([1e-2]))
+    isl.add_cost(a)
+    isl.add_cost(b)
+    isl.add_constraint(copra.ControlBoundConstraint(Fx.uLower, Fx.uUpper))
+    isl.reset_initial_state_cost(np.identity(2), np.array([3.0, -7.0]))  # pulls x0 away; the default bounds hold it
+    assert isl.solve()
+    assert np.abs(isl.initial_state() - Fx.x0).max() <= 1e-9

@@ -31,3 +31,30 @@ def active_set(iact, nact=None):
     if nact is not None:
         iact = iact[:nact]
     return set(int(i) for i in iact if i > 0)
+
+
+def active_set_excused(got, o):
+    """active sets are compared as SETS of 1-based indices in the [eq | ineq | upper | lower] space.  A row
+    that is in exactly one of the two sets is excused only when it is WEAKLY active at the oracle's solution -- both its
+    slack and its multiplier vanish (|s_i| < 1e-9 and u_i < 1e-9, scaled) -- because then the two sets describe the same
+    optimum and membership is decided by last-bit rounding.  Returns the number of excused rows; raises otherwise."""
+    ref = active_set(o["iact"])
+    diff = set(got) ^ ref
+    if not diff:
+        return 0
+    x = np.asarray(o["x"], float)
+    n = x.shape[0]
+    Aeq, Aineq = np.asarray(o["Aeq"], float).reshape(-1, n), np.asarray(o["Aineq"], float).reshape(-1, n)
+    G = np.vstack([Aeq, Aineq, np.eye(n), -np.eye(n)])
+    with np.errstate(invalid="ignore"):
+        h = np.concatenate([np.asarray(o["beq"], float), np.asarray(o["bineq"], float), np.asarray(o["ub"], float),
+                            -np.asarray(o["lb"], float)])
+    grad = np.asarray(o["Q"], float) @ x + np.asarray(o["c"], float)
+    s_scale, u_scale = max(1.0, np.abs(x).max()), max(1.0, np.abs(grad).max())
+    lag = np.asarray(o["lagr"], float)
+    for i in sorted(diff):
+        k = i - 1
+        slack = h[k] - G[k] @ x
+        assert abs(slack) < 1e-9 * s_scale and abs(lag[k]) < 1e-9 * u_scale, \
+            "active sets differ at row %d which is not weakly active (slack %.3e, multiplier %.3e)" % (i, slack, lag[k])
+    return len(diff)
