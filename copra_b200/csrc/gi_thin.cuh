@@ -288,7 +288,7 @@ __device__ __forceinline__ void gt_q1_row_dots(const GtWork& W, int ld, int q1s,
         }
     }
     if (G == 1) {
-        if (pr < pairs) { out[2 * pr] = sx0 + sx1; out[2 * pr + 1] = sy0 + sy1; }
+        if (g == 0 && pr < pairs) { out[2 * pr] = sx0 + sx1; out[2 * pr + 1] = sy0 + sy1; } // threads past the last full group idle
         return;
     }
     if (g < G && pr < pairs) {
@@ -497,6 +497,7 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
 #ifdef GT_PROFILE
     long long gt_acc[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
     long long gt_t0 = clock64();
+    const long long gt_tstart = gt_t0;
     int gt_reorth = 0;
 #endif
 
@@ -779,7 +780,7 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
     }
     __syncthreads();
 #ifdef GT_PROFILE
-    if (tid == 0 && (b % 97) == 0)
+    if (tid == 0 && ((b % 97) == 0 || clock64() - gt_tstart > 60000000LL))
         printf("GTPROF b=%d n=%d iters=%d drops=%d nact=%d reorth=%d | init %lld prod %lld sel %lld normal+Jt'a %lld q1 %lld Jz+S %lld step+add %lld drop %lld\n",
             b, n, iter0, iter1, nact, gt_reorth, gt_acc[0], gt_acc[1], gt_acc[2], gt_acc[3], gt_acc[4], gt_acc[5], gt_acc[6], gt_acc[7]);
 #endif
