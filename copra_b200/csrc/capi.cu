@@ -485,14 +485,33 @@ int run_gt(copra_b200_handle* h, double* x, int* status, int* iters, int* nact, 
     if ((rc = ws(h, "gt_pd", count, &pd))) return rc;
     if ((rc = ws(h, "gt_ws", size_t(plan.grid) * plan.ws_stride, &wsp))) return rc;
     if ((rc = ws(h, "counter", 2, &counter))) return rc;
+    // batch-invariant system and Hessian: Dpsi = Jt' Psi' once per build (one Toeplitz fill + one DMMA GEMM)
+    const bool use_dpsi = P.sQ == 0 && P.A.s == 0 && P.B.s == 0 && !getenv("COPRA_B200_THIN_NO_DPSI");
+    double *psit = nullptr, *dpsi = nullptr;
+    if (use_dpsi) {
+        if ((rc = ws(h, "gt_psit", n * size_t(P.X), &psit))) return rc;
+        if ((rc = ws(h, "gt_dpsi", ldj * size_t(P.X), &dpsi))) return rc;
+    }
     if (!h->factor_valid) {
         cudaError_t e = gt_factor_launch(DArr{ P.Q, P.sQ }, P.nvar, T.ld, int(count), Jt, JtT, pd, sms, h->stream);
         if (e != cudaSuccess) return fail(h, COPRA_B200_E_CUDA, "gt_factor_launch: %s", cudaGetErrorString(e));
         h->launches += 1; h->call_launches += 1;
+        if (use_dpsi) {
+            e = gt_psit_fill_launch(P.Gs, psit, P.nx, P.nu, P.N, h->stream);
+            if (e != cudaSuccess) return fail(h, COPRA_B200_E_CUDA, "gt_psit_fill_launch: %s", cudaGetErrorString(e));
+            h->launches += 1; h->call_launches += 1;
+            LAUNCHED(dgemm_dmma_launch(1, P.nvar, P.X, P.nvar, 1.0, Jt, T.ld, 0, psit, P.nvar, 0, 0.0, dpsi, T.ld, 0, 1, h->stream));
+        }
         h->factor_valid = true;
     }
+    T.Dpsi = use_dpsi ? dpsi : nullptr;
+    T.nx = P.nx; T.X = P.X;
     CU(cudaMemsetAsync(counter, 0, 2 * sizeof(int), h->stream));
-    for (int k = 0; k < P.nfam; ++k) { T.fam[k].EGx = P.fam[k].EGx; T.fam[k].sEGx = P.fam[k].sEGx; }
+    for (int k = 0; k < P.nfam; ++k) {
+        T.fam[k].EGx = P.fam[k].EGx; T.fam[k].sEGx = P.fam[k].sEGx;
+        T.fam[k].E = P.fam[k].hasE ? P.fam[k].E : DArr{ nullptr, 0 };
+        T.fam[k].G = P.fam[k].hasG ? P.fam[k].G : DArr{ nullptr, 0 };
+    }
     const long long nn = (long long)(ldj * n);
     T.Jt = DArr{ Jt, P.sQ ? nn : 0 };
     T.JtT = DArr{ JtT, P.sQ ? nn : 0 };

@@ -39,6 +39,7 @@ struct GtFam {
     int tab;                          // offset of this family's table in the shared-memory table area (doubles)
     const double* EGx;                // r x nu x (N+1) per instance: block kk = E A^(kk-1) B (kk >= 1), G | 0 (kk == 0)
     long long sEGx;
+    DArr E, G;                        // the family's own r x nx / r x nu blocks (null when absent): used with Dpsi
 };
 
 struct GtBatch {
@@ -49,6 +50,11 @@ struct GtBatch {
     int q1s;            // columns of Q1 held in shared memory (the rest lives in the global workspace)
     double reorth;      // second Gram-Schmidt pass when |zt|^2 < reorth * |d|^2
     GtFam fam[kMaxFam];
+    // Batch-invariant system AND Hessian: Dpsi = Jt' Psi' (ld x X, column-major) is formed once per batch by the DMMA GEMM,
+    // and d = Jt' a for the step-size row (family, step, line) is  sum_e E[line,e] Dpsi[:, step nx + e] + sum_b G[line,b] Jt'[:, step nu + b]
+    // -- nx + nu short column reads instead of a triangular mat-vec over Jt (null: per-instance systems, mat-vec path)
+    const double* Dpsi;
+    int nx, X;
     DArr Jt, JtT;       // R^-1 column-major (entries i <= j of column j) and its transpose (entries j >= i of column i)
     const int* pd;      // 1 = Hessian positive definite, per distinct Hessian
     int pd_stride;      // 0 (shared) or 1
@@ -380,7 +386,24 @@ __device__ __forceinline__ void gt_products(const GtBatch& B, const GtWork& W)
             double acc[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+            // interior lags: every (step, line, lag) of the tile exists -> no predicates; the <= 3 lags past `ib` and ragged
+            // tiles (last steps / lines of a family) take the guarded loop
+            const bool full = (ib + 3 < F.i1) && (l0 + 3 < r);
+            const int kk_in_lo = full ? max(kk_lo, ib + 3 - (N - 1)) : kk_hi + 1, kk_in_hi = full ? min(ib, kk_hi) : kk_hi;
+            for (int kk = kk_in_lo + lane; kk <= kk_in_hi; kk += 32) {
+                for (int bb = 0; bb < nu; ++bb) {
+                    const double* tp = tab + size_t(l0 + r * bb) * ldk + kk;
+                    const double* xp = W.xt + bb * N + (ib - kk);
+                    const double t0 = tp[0], t1 = tp[ldk], t2 = tp[2 * size_t(ldk)], t3 = tp[3 * size_t(ldk)];
+                    const double x0 = xp[0], x1 = xp[1], x2 = xp[2], x3 = xp[3];
+                    acc[0] = fma(t0, x0, acc[0]); acc[1] = fma(t1, x0, acc[1]); acc[2] = fma(t2, x0, acc[2]); acc[3] = fma(t3, x0, acc[3]);
+                    acc[4] = fma(t0, x1, acc[4]); acc[5] = fma(t1, x1, acc[5]); acc[6] = fma(t2, x1, acc[6]); acc[7] = fma(t3, x1, acc[7]);
+                    acc[8] = fma(t0, x2, acc[8]); acc[9] = fma(t1, x2, acc[9]); acc[10] = fma(t2, x2, acc[10]); acc[11] = fma(t3, x2, acc[11]);
+                    acc[12] = fma(t0, x3, acc[12]); acc[13] = fma(t1, x3, acc[13]); acc[14] = fma(t2, x3, acc[14]); acc[15] = fma(t3, x3, acc[15]);
+                }
+            }
             for (int kk = kk_lo + lane; kk <= kk_hi; kk += 32) {
+                if (full && kk >= kk_in_lo && kk <= kk_in_hi) continue; // done above
                 for (int bb = 0; bb < nu; ++bb) {
                     const double* tp = tab + size_t(l0 + r * bb) * ldk + kk;
                     const double* xp = W.xt + bb * N + (ib - kk);
@@ -592,8 +615,24 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
                 } else {
                     for (int k = tid; k < n; k += T) W.av[k] = sg * gAin[(nvl - meq) + size_t(k) * m];
                 }
-                __syncthreads();
-                gt_trap_mv<false>(JtT, ld, n, supp, W.av, W.d, W.part);
+                if (B.structured && B.Dpsi) {
+                    int fi, step, line;
+                    gt_locate(B, nvl, fi, step, line);
+                    const GtFam& F = B.fam[fi];
+                    const double* Ef = F.E.p ? F.E.at(b) : nullptr;
+                    const double* Gf = (F.G.p && step < B.N) ? F.G.at(b) : nullptr;
+                    const double* dp = B.Dpsi + size_t(step) * B.nx * ld;
+                    const double* jp = JtT + size_t(step) * B.nu * ld;
+                    for (int k = tid; k < n; k += T) {
+                        double acc = 0.0;
+                        if (Ef) for (int e = 0; e < B.nx; ++e) acc = fma(Ef[line + e * F.rows], __ldg(dp + k + size_t(e) * ld), acc);
+                        if (Gf) for (int e = 0; e < B.nu; ++e) acc = fma(Gf[line + e * F.rows], __ldg(jp + k + size_t(e) * ld), acc);
+                        W.d[k] = sg * acc;
+                    }
+                } else {
+                    __syncthreads();
+                    gt_trap_mv<false>(JtT, ld, n, supp, W.av, W.d, W.part);
+                }
             } else {
                 const int j = nvl - mg;
                 if (j < n) { bj = j; bsign = -1.0; }
@@ -807,5 +846,6 @@ size_t gt_factor_smem(int n);
 // factor `count` Hessians Q (n x n each): Jt / JtT receive count * n * n doubles, pd count flags
 cudaError_t gt_factor_launch(DArr Q, int n, int ld, int count, double* Jt, double* JtT, int* pd, int sms, cudaStream_t st);
 cudaError_t gt_launch(const GtBatch& B, const GtPlan& plan, cudaStream_t st);
+cudaError_t gt_psit_fill_launch(const double* Gs, double* PsiT, int nx, int nu, int N, cudaStream_t st);
 
 } // namespace cb

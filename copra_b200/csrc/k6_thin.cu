@@ -53,6 +53,25 @@ __global__ void __launch_bounds__(512, 1) gt_factor_kernel(DArr Q, int n, int ld
     }
 }
 
+// Psi' (nU x X, column-major) of ONE system from its compact first block column Gs: Psi[s nx + a, j nu + b] = (A^(s-1-j) B)[a, b]
+// for j < s, zero otherwise (src/PreviewSystem.cpp:63-71).  Right-hand operand of Dpsi = Jt' Psi'.
+__global__ void gt_psit_fill_kernel(const double* __restrict__ Gs, double* __restrict__ PsiT, int nx, int nu, int N)
+{
+    const int nU = nu * N, X = nx * (N + 1);
+    const long long total = (long long)nU * X;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int i = int(idx % nU), c = int(idx / nU);
+        const int j = i / nu, bb = i - j * nu, st = c / nx, a = c - st * nx;
+        PsiT[idx] = (j < st) ? Gs[size_t(st - 1 - j) * nx + a + size_t(bb) * N * nx] : 0.0;
+    }
+}
+
+cudaError_t gt_psit_fill_launch(const double* Gs, double* PsiT, int nx, int nu, int N, cudaStream_t st)
+{
+    gt_psit_fill_kernel<<<296, 256, 0, st>>>(Gs, PsiT, nx, nu, N);
+    return cudaGetLastError();
+}
+
 template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) gi_thin_kernel(const __grid_constant__ GtBatch B)
 {
