@@ -15,7 +15,7 @@ $(CSRC)/%.o: $(CSRC)/%.cu $(HDRS)
 
 $(LIB): $(OBJS)
 	mkdir -p copra_b200/lib
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart static
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart static -ldl
 
 oracle:
 	$(MAKE) -C oracle -s

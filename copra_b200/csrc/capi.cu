@@ -10,6 +10,8 @@
 #include "gi_thin.cuh"
 #include "slice.h"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <cfloat>
 #include <cmath>
 #include <cstdarg>
@@ -62,6 +64,7 @@ struct copra_b200_handle {
     bool rows_filled = false;  // Aeq / Aineq of the last build are materialised (the structured solver never reads them)
     bool use_thin = false;     // the last build is solved by the thin kernel (gi_thin.cuh)
     const char* solver = "";   // K5+K6 kernel(s) of the last solve
+    bool nvtx_open = false;    // an NVTX stage range is open on the calling thread
     GtBatch gt{};
     GtPlan gtplan{};
     BuildParams bp{};
@@ -125,8 +128,14 @@ int pin_reserve(copra_b200_handle* h, Buf& b, size_t bytes)
     return 0;
 }
 
+// Stage boundaries: CUDA event k on the stream (copra_b200_last_timing) + an NVTX range per stage for Nsight timelines
+// (the reference's only tracing is the two wall-clock timers of src/LMPC.cpp:82-99).
 int record(copra_b200_handle* h, int k)
 {
+    static const char* const kStage[6] = { "copra_b200: H2D parameters", "copra_b200: K1 condense", "copra_b200: K2-K4 assemble",
+        "copra_b200: K5+K6 solve", "copra_b200: K7 rollout", "copra_b200: D2H results" };
+    if (h->nvtx_open) { nvtxRangePop(); h->nvtx_open = false; }
+    if (k >= 0 && k < 6) { nvtxRangePushA(kStage[k]); h->nvtx_open = true; }
     if (!h->ev[k]) CU(cudaEventCreate(&h->ev[k]));
     CU(cudaEventRecord(h->ev[k], h->stream));
     h->ev_valid[k] = true;

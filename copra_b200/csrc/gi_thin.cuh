@@ -378,8 +378,12 @@ __device__ __forceinline__ void gt_products(const GtBatch& B, const GtWork& W)
         const int nsb = (ns + 3) >> 2, nrg = (r + 3) >> 2, ntask = nsb * nrg;
         const double* tab = W.tab + F.tab;
         double* out = W.sl + (F.is_eq ? 0 : B.meq) + F.row_off;
-        int t = (wp - task0 % nw + nw) % nw;
-        for (; t < ntask; t += nw) {
+        // tiles are dealt longest first in a snake (round 0: warp 0..nw-1, round 1: warp nw-1..0, ...): the work of a tile
+        // grows linearly with its step, so the snake keeps the per-warp totals within one tile of each other
+        const int w0 = (wp - task0 % nw + nw) % nw;
+        for (int rnd = 0; rnd * nw < ntask; ++rnd) {
+            const int t = rnd * nw + ((rnd & 1) ? nw - 1 - w0 : w0);
+            if (t >= ntask) continue;
             const int sb = nsb - 1 - t / nrg, rg = t % nrg;
             const int ib = F.i0 + 4 * sb, l0 = 4 * rg;
             const int kk_lo = max(0, ib - (N - 1)), kk_hi = min(ib + 3, F.i1 - 1);

@@ -1054,6 +1054,20 @@ public:
     void initialStateBounds(copra_b200_array lo, copra_b200_array up) { p_.x0lb = lo; p_.x0ub = up; }
     int addCost(const copra_b200_cost& c) { costs_.push_back(c); return int(costs_.size()) - 1; }
     int addConstraint(const copra_b200_constraint& c) { cstrs_.push_back(c); return int(cstrs_.size()) - 1; }
+    ~BatchedLMPC() { if (multi_) copra_b200_multi_destroy(multi_); }
+    BatchedLMPC(const BatchedLMPC&) = delete;
+    BatchedLMPC& operator=(const BatchedLMPC&) = delete;
+    // Data-parallel sharding: split the batch by instance index over these CUDA devices (one engine handle
+    // and host thread per entry; an empty list = every visible device).  HOST arrays only.  Results are bitwise those of
+    // a single-device solve.
+    void useDevices(const std::vector<int>& devices)
+    {
+        if (p_.memory != COPRA_B200_HOST) COPRA_DOMAIN_ERROR("BatchedLMPC::useDevices takes HOST arrays (each shard is uploaded to its own device)");
+        if (multi_) { copra_b200_multi_destroy(multi_); multi_ = nullptr; }
+        const int rc = copra_b200_multi_create(devices.empty() ? nullptr : devices.data(), int(devices.size()), &multi_);
+        if (rc) throw std::runtime_error("copra_b200_multi_create failed (no usable sm_100 CUDA device; there is no CPU fallback)");
+    }
+    int nrDevices() const { return multi_ ? copra_b200_multi_size(multi_) : 1; }
     copra_b200_sizes sizes()
     {
         copra_b200_sizes s{};
@@ -1071,6 +1085,17 @@ public:
         copra_b200_results R{};
         R.control = controls_.data(); R.trajectory = trajectories_.data(); R.status = status_.data(); R.iters = iterations_.data();
         R.nact = nact_.data(); R.iact = iact_.data(); R.memory = COPRA_B200_HOST;
+        if (multi_) {
+            if (copra_b200_multi_lmpc_run(multi_, finish(), &R)) throw std::runtime_error(copra_b200_multi_last_error(multi_));
+            solveTime_ = 0.0;
+            for (int g = 0; g < copra_b200_multi_size(multi_); ++g) { // slowest shard's K5+K6 time
+                copra_b200_timing tm{};
+                if (copra_b200_multi_timing(multi_, g, &tm, nullptr) == 0) solveTime_ = std::max(solveTime_, double(tm.solve_ms) * 1e-3);
+            }
+            multiBuilt_ = true;
+            solveAndBuildTime_ = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+            return int(std::count(status_.begin(), status_.end(), 0));
+        }
         b200::check(copra_b200_lmpc_run(b200::handle(), finish(), &R));
         myEpoch_ = ++b200::buildEpoch();
         copra_b200_timing tm{};
@@ -1083,7 +1108,17 @@ public:
     // states change; condensing, Q and the constraint matrices stay resident on the device.  LMPC mode only.
     int resolve(copra_b200_array x0)
     {
-        if (myEpoch_ != b200::buildEpoch() || p_.batch > 65535 || p_.initial_state) {
+        if (multi_ && multiBuilt_ && !p_.initial_state && p_.batch <= 65535) {
+            const auto t0 = std::chrono::high_resolution_clock::now();
+            copra_b200_results R{};
+            R.control = controls_.data(); R.trajectory = trajectories_.data(); R.status = status_.data(); R.iters = iterations_.data();
+            R.nact = nact_.data(); R.iact = iact_.data(); R.memory = COPRA_B200_HOST;
+            if (copra_b200_multi_lmpc_resolve(multi_, x0, &R)) throw std::runtime_error(copra_b200_multi_last_error(multi_));
+            p_.x0 = x0;
+            solveAndBuildTime_ = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+            return int(std::count(status_.begin(), status_.end(), 0));
+        }
+        if (multi_ || myEpoch_ != b200::buildEpoch() || p_.batch > 65535 || p_.initial_state) {
             // another controller used the process-wide engine since, the batch was processed in chunks (only the last chunk
             // is resident), or x0 is a decision variable: full rebuild
             p_.x0 = x0;
@@ -1124,6 +1159,8 @@ private:
     std::vector<int> status_, iterations_, nact_, iact_;
     double solveTime_ = 0, solveAndBuildTime_ = 0;
     unsigned long myEpoch_ = ~0ul;
+    copra_b200_multi* multi_ = nullptr;
+    bool multiBuilt_ = false;
 };
 
 } // namespace copra

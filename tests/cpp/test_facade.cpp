@@ -641,6 +641,18 @@ static void batchedEntry()
     same = true;
     for (int i = 0; i < N; ++i) if (ctl.controls()[size_t(7) * N + i] != one.control()(i)) same = false;
     REQUIRE(same);
+    // data-parallel sharding: the same batch over three engine handles (device 0 thrice when the box has one
+    // GPU; distinct devices otherwise) -- ragged shards of 22 / 22 / 20 instances, results BITWISE the single-handle ones
+    const std::vector<double> ref_u = ctl.controls(), ref_x = ctl.trajectories();
+    const std::vector<int> ref_it = ctl.iterations();
+    const int ndev = copra_b200_device_count();
+    ctl.useDevices(ndev >= 3 ? std::vector<int>{ 0, 1, 2 } : std::vector<int>{ 0, 0, 0 });
+    REQUIRE(ctl.nrDevices() == 3);
+    REQUIRE(ctl.solve() == batch);                                  // full solve of the x0 batch, sharded
+    REQUIRE(ctl.resolve(copra::b200::arr(x1.data(), 2)) == batch); // sharded receding-horizon step
+    REQUIRE(ctl.controls() == ref_u);
+    REQUIRE(ctl.trajectories() == ref_x);
+    REQUIRE(ctl.iterations() == ref_it);
 }
 
 int main(int argc, char** argv)
