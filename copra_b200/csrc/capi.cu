@@ -537,7 +537,28 @@ int run_gt(copra_b200_handle* h, double* x, int* status, int* iters, int* nact, 
     T.vsmall = h->vsmall;
     T.max_iter = 50 * (P.meq + P.mineq + 2 * P.nvar) + 100;
     h->solver = "gt_factor_kernel + gi_thin_kernel";
-    cudaError_t e = gt_launch(T, plan, h->stream);
+    // few waves of instances per resident CTA: the step ends with the slowest instance, so rank the instances by the number
+    // of constraints violated at their unconstrained minimiser (one cheap prepass) and start the heaviest first
+    T.prekey = nullptr; T.preidx = nullptr; T.order = nullptr;
+    const bool lpt = P.batch > plan.grid && P.batch <= 24 * plan.grid && !getenv("COPRA_B200_THIN_NO_LPT");
+    cudaError_t e;
+    if (lpt) {
+        int *keys = nullptr, *keys2 = nullptr, *idx = nullptr, *order = nullptr;
+        void* tmp = nullptr;
+        const size_t tb = gt_sort_temp_bytes(P.batch);
+        if ((rc = ws(h, "gt_keys", 4 * size_t(P.batch), &keys))) return rc;
+        if ((rc = dev_reserve(h, "gt_sorttmp", tb, &tmp))) return rc;
+        keys2 = keys + P.batch; idx = keys + 2 * size_t(P.batch); order = keys + 3 * size_t(P.batch);
+        T.prekey = keys; T.preidx = idx;
+        e = gt_launch(T, plan, h->stream);
+        if (e != cudaSuccess) return fail(h, COPRA_B200_E_CUDA, "gt_launch (prepass): %s", cudaGetErrorString(e));
+        e = gt_sort_launch(keys, keys2, idx, order, P.batch, tmp, tb, h->stream);
+        if (e != cudaSuccess) return fail(h, COPRA_B200_E_CUDA, "gt_sort_launch: %s", cudaGetErrorString(e));
+        h->launches += 2; h->call_launches += 2;
+        CU(cudaMemsetAsync(counter, 0, 2 * sizeof(int), h->stream));
+        T.prekey = nullptr; T.preidx = nullptr; T.order = order;
+    }
+    e = gt_launch(T, plan, h->stream);
     if (e != cudaSuccess) return fail(h, COPRA_B200_E_CUDA, "gt_launch: %s", cudaGetErrorString(e));
     h->launches += 1; h->call_launches += 1;
     return 0;

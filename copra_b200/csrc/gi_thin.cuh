@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "engine.cuh"
 #include "gi_solver.cuh"
+#include <cooperative_groups.h>
 #ifdef GT_PROFILE
 #include <cstdio>
 #define GT_T(k) do { const long long t1_ = clock64(); gt_acc[k] += t1_ - gt_t0; gt_t0 = t1_; } while (0)
@@ -33,6 +34,36 @@
 #endif
 
 namespace cb {
+
+namespace cg = cooperative_groups;
+
+// Communication policy of the thin solver.
+//   GtSolo : one CTA per instance (the throughput configuration: C3).
+//   GtClus : one thread-block CLUSTER per instance (the latency configuration for n > 512 with per-instance factors: C5, whose
+//            step is the latency of its heaviest instance).  Every heavy stream (the factor, Q1, S, the Toeplitz products) is
+//            split over the CTAs; every small vector is REPLICATED: a producer stores its entries at the same shared-memory
+//            address of every CTA (DSMEM) with put(), and one cluster barrier publishes them.  All CTAs run the same control
+//            flow on bitwise identical replicas, so no decision is ever exchanged.  Q1 and S live in global memory (L2) and are
+//            written in disjoint pieces; the cluster barrier (release / acquire at cluster scope) orders those writes too.
+struct GtSolo {
+    static constexpr bool multi = false;
+    __device__ __forceinline__ int rank() const { return 0; }
+    __device__ __forceinline__ int size() const { return 1; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    template <class T> __device__ __forceinline__ void put(T* p, T v) const { *p = v; }
+};
+struct GtClus {
+    static constexpr bool multi = true;
+    cg::cluster_group cl;
+    int r, c;
+    __device__ __forceinline__ int rank() const { return r; }
+    __device__ __forceinline__ int size() const { return c; }
+    __device__ __forceinline__ void sync() const { cl.sync(); }
+    template <class T> __device__ __forceinline__ void put(T* p, T v) const
+    {
+        for (int k = 0; k < c; ++k) *cl.map_shared_rank(p, k) = v;
+    }
+};
 
 struct GtFam {
     int rows, i0, i1, is_eq, row_off; // row_off: first row inside Aeq (is_eq) or Aineq
@@ -66,6 +97,13 @@ struct GtBatch {
     int* counter;
     double vsmall;
     int max_iter;
+    // Scheduling of heavy-tailed batches (iteration counts of C5 range from 10 to > 2000 passes): a PREPASS launch computes,
+    // per instance, the number of constraints violated at the unconstrained minimiser (correlation with the work: 0.92) into
+    // `prekey`; the solve launch then pulls instances in `order` (descending key: longest first), so the heaviest instance
+    // starts at t = 0 instead of wherever the index order put it.  Both null: index order.
+    int* prekey;
+    int* preidx;
+    const int* order;
 };
 
 struct GtLayout {
@@ -145,22 +183,26 @@ __device__ inline GtWork gt_carve(const GtLayout& L, unsigned char* smem, double
 //   ZMODE : z[i] = sum_{j >= i} Jt[i, j] v[j]      on M = Jt  : clo = 64 k, chi = n      (stored zeros below the diagonal)
 //   !ZMODE: d[j] = sum_{i <= j, i < supp} Jt[i, j] a[i]  on M = JtT : clo = 0, chi = min(64 k + 64, supp)
 // Contains one __syncthreads; the caller syncs before reading `out`.
-template <bool ZMODE>
-__device__ __forceinline__ void gt_trap_mv(const double* __restrict__ M, int ld, int n, int supp, const double* __restrict__ vec,
+// With a cluster the 64-row chunks are dealt to the CTAs in a snake (the work of a chunk is linear in its index), each CTA
+// runs the task list of ITS chunks and publishes their rows to every replica.
+template <bool ZMODE, class CL>
+__device__ __forceinline__ void gt_trap_mv(const CL& cl, const double* __restrict__ M, int ld, int n, int supp, const double* __restrict__ vec,
     double* __restrict__ out, double* __restrict__ part)
 {
     const int lane = lane_id(), wp = warp_id(), nw = blockDim.x >> 5;
-    const int nc = (n + 63) >> 6;
+    const int nc = (n + 63) >> 6, C = cl.size(), me = cl.rank();
     auto clo = [&](int k) { return ZMODE ? (k << 6) : 0; };
     auto chi = [&](int k) { return ZMODE ? n : min(min((k << 6) + 64, supp), n); };
+    auto mine = [&](int k) { const int rr = k % (2 * C); return (rr < C ? rr : 2 * C - 1 - rr) == me; };
     int tot = 0;
-    for (int k = 0; k < nc; ++k) tot += chi(k) - clo(k);
+    for (int k = 0; k < nc; ++k) if (mine(k)) tot += chi(k) - clo(k);
     const int cw = max(64, (((tot + 2 * nw - 1) / (2 * nw)) + 63) & ~63); // columns per task
     int ntask = 0;
-    for (int k = 0; k < nc; ++k) ntask += (chi(k) - clo(k) + cw - 1) / cw;
+    for (int k = 0; k < nc; ++k) if (mine(k)) ntask += (chi(k) - clo(k) + cw - 1) / cw;
     for (int t = wp; t < ntask; t += nw) {
         int k = 0, t0 = 0;
         for (;; ++k) {
+            if (!mine(k)) continue;
             const int nt = (chi(k) - clo(k) + cw - 1) / cw;
             if (t < t0 + nt) break;
             t0 += nt;
@@ -201,24 +243,27 @@ __device__ __forceinline__ void gt_trap_mv(const double* __restrict__ M, int ld,
     __syncthreads();
     for (int r = threadIdx.x; r < n; r += blockDim.x) {
         const int k = r >> 6;
+        if (!mine(k)) continue;
         int t0 = 0;
-        for (int kk = 0; kk < k; ++kk) t0 += (chi(kk) - clo(kk) + cw - 1) / cw;
+        for (int kk = 0; kk < k; ++kk) if (mine(kk)) t0 += (chi(kk) - clo(kk) + cw - 1) / cw;
         const int nt = (chi(k) - clo(k) + cw - 1) / cw;
         double sum = 0.0;
         for (int q = 0; q < nt; ++q) sum += part[(size_t(t0 + q) << 6) + (r & 63)];
-        out[r] = sum;
+        cl.put(out + r, sum);
     }
 }
 
 // out[c] = Q1[:, c] . vec for c in [0, nact): an 8-lane group per column (128-bit loads, three shuffles per column), head
 // columns from shared memory, the rest from the global workspace
-__device__ __forceinline__ void gt_q1_col_dots(const GtWork& W, int n, int ld, int q1s, int nact, const double* __restrict__ vec,
+template <class CL>
+__device__ __forceinline__ void gt_q1_col_dots(const CL& cl, const GtWork& W, int n, int ld, int q1s, int nact, const double* __restrict__ vec,
     double* __restrict__ out)
 {
     const int lane = lane_id(), wp = warp_id(), nw = blockDim.x >> 5;
     const int g8 = lane >> 3, l8 = lane & 7;
     (void)n;
-    for (int cb = 4 * wp; cb < nact; cb += 4 * nw) {
+    // blocks of four columns are dealt over the CTAs first, then over the warps
+    for (int cb = 4 * (cl.rank() + cl.size() * wp); cb < nact; cb += 4 * nw * cl.size()) {
         const int c = cb + g8;
         const bool on = c < nact;
         const double* col = (c < q1s ? W.Q1s : W.Q1) + size_t(on ? c : 0) * ld;
@@ -245,78 +290,152 @@ __device__ __forceinline__ void gt_q1_col_dots(const GtWork& W, int n, int ld, i
         q += __shfl_xor_sync(0xffffffffu, q, 4);
         q += __shfl_xor_sync(0xffffffffu, q, 2);
         q += __shfl_xor_sync(0xffffffffu, q, 1);
-        if (on && l8 == 0) out[c] = q;
+        if (on && l8 == 0) cl.put(out + c, q);
     }
 }
 
 // out[r] = sum_{c < nact} Q1[r, c] * vec[c]: a thread owns a PAIR of rows (one 128-bit load per column), the column range
 // is split over G = T / round32(ld / 2) thread groups whose partial sums meet in `part` (fixed order).  One __syncthreads
 // inside when G > 1; the caller syncs before reading `out`.
-__device__ __forceinline__ void gt_q1_row_dots(const GtWork& W, int ld, int q1s, int nact, const double* __restrict__ vec,
+template <class CL>
+__device__ __forceinline__ void gt_q1_row_dots(const CL& cl, const GtWork& W, int ld, int q1s, int nact, const double* __restrict__ vec,
     double* __restrict__ out, double* __restrict__ part)
 {
     const int tid = threadIdx.x, T = blockDim.x;
-    const int pairs = ld >> 1, rp = max(32, round32(pairs));
+    const int all = ld >> 1, per = (all + cl.size() - 1) / cl.size();          // row pairs: a contiguous slab per CTA
+    const int p0 = min(all, cl.rank() * per), pairs = min(all, p0 + per) - p0;
+    const int rp = max(32, round32(pairs));
     const int G = max(1, T / rp);
-    if (T < rp) { // more row pairs than threads: loop over pairs, all columns per thread
+    auto colp = [&](int c) -> const double* { return (c < q1s ? W.Q1s : W.Q1) + size_t(c) * ld + 2 * p0; };
+    if (T < rp) { // more row pairs than threads: loop over pairs, all columns per thread (four loads in flight)
         for (int pr = tid; pr < pairs; pr += T) {
-            double sx = 0.0, sy = 0.0;
-            for (int c = 0; c < nact; ++c) {
-                const double* col = (c < q1s ? W.Q1s : W.Q1) + size_t(c) * ld;
-                const double2 a = *reinterpret_cast<const double2*>(col + 2 * pr);
-                sx = fma(a.x, vec[c], sx);
-                sy = fma(a.y, vec[c], sy);
+            double2 s0 = make_double2(0.0, 0.0), s1 = s0, s2 = s0, s3 = s0;
+            int c = 0;
+            for (; c + 3 < nact; c += 4) {
+                const double2 a0 = *reinterpret_cast<const double2*>(colp(c) + 2 * pr), a1 = *reinterpret_cast<const double2*>(colp(c + 1) + 2 * pr);
+                const double2 a2 = *reinterpret_cast<const double2*>(colp(c + 2) + 2 * pr), a3 = *reinterpret_cast<const double2*>(colp(c + 3) + 2 * pr);
+                s0.x = fma(a0.x, vec[c], s0.x); s0.y = fma(a0.y, vec[c], s0.y);
+                s1.x = fma(a1.x, vec[c + 1], s1.x); s1.y = fma(a1.y, vec[c + 1], s1.y);
+                s2.x = fma(a2.x, vec[c + 2], s2.x); s2.y = fma(a2.y, vec[c + 2], s2.y);
+                s3.x = fma(a3.x, vec[c + 3], s3.x); s3.y = fma(a3.y, vec[c + 3], s3.y);
             }
-            out[2 * pr] = sx;
-            out[2 * pr + 1] = sy;
+            for (; c < nact; ++c) {
+                const double2 a0 = *reinterpret_cast<const double2*>(colp(c) + 2 * pr);
+                s0.x = fma(a0.x, vec[c], s0.x); s0.y = fma(a0.y, vec[c], s0.y);
+            }
+            cl.put(out + 2 * (p0 + pr), (s0.x + s1.x) + (s2.x + s3.x));
+            cl.put(out + 2 * (p0 + pr) + 1, (s0.y + s1.y) + (s2.y + s3.y));
         }
         return;
     }
     const int g = tid / rp, pr = tid - g * rp;
-    double sx0 = 0.0, sy0 = 0.0, sx1 = 0.0, sy1 = 0.0;
+    double2 s0 = make_double2(0.0, 0.0), s1 = s0, s2 = s0, s3 = s0;
     if (g < G && pr < pairs) {
         int c = g;
-        for (; c + G < nact; c += 2 * G) {
-            const double* col0 = (c < q1s ? W.Q1s : W.Q1) + size_t(c) * ld;
-            const double* col1 = (c + G < q1s ? W.Q1s : W.Q1) + size_t(c + G) * ld;
-            const double2 a = *reinterpret_cast<const double2*>(col0 + 2 * pr);
-            const double2 e = *reinterpret_cast<const double2*>(col1 + 2 * pr);
-            sx0 = fma(a.x, vec[c], sx0);
-            sy0 = fma(a.y, vec[c], sy0);
-            sx1 = fma(e.x, vec[c + G], sx1);
-            sy1 = fma(e.y, vec[c + G], sy1);
+        for (; c + 3 * G < nact; c += 4 * G) {
+            const double2 a0 = *reinterpret_cast<const double2*>(colp(c) + 2 * pr), a1 = *reinterpret_cast<const double2*>(colp(c + G) + 2 * pr);
+            const double2 a2 = *reinterpret_cast<const double2*>(colp(c + 2 * G) + 2 * pr), a3 = *reinterpret_cast<const double2*>(colp(c + 3 * G) + 2 * pr);
+            s0.x = fma(a0.x, vec[c], s0.x); s0.y = fma(a0.y, vec[c], s0.y);
+            s1.x = fma(a1.x, vec[c + G], s1.x); s1.y = fma(a1.y, vec[c + G], s1.y);
+            s2.x = fma(a2.x, vec[c + 2 * G], s2.x); s2.y = fma(a2.y, vec[c + 2 * G], s2.y);
+            s3.x = fma(a3.x, vec[c + 3 * G], s3.x); s3.y = fma(a3.y, vec[c + 3 * G], s3.y);
         }
-        if (c < nact) {
-            const double* col0 = (c < q1s ? W.Q1s : W.Q1) + size_t(c) * ld;
-            const double2 a = *reinterpret_cast<const double2*>(col0 + 2 * pr);
-            sx0 = fma(a.x, vec[c], sx0);
-            sy0 = fma(a.y, vec[c], sy0);
+        for (; c < nact; c += G) {
+            const double2 a0 = *reinterpret_cast<const double2*>(colp(c) + 2 * pr);
+            s0.x = fma(a0.x, vec[c], s0.x); s0.y = fma(a0.y, vec[c], s0.y);
         }
     }
+    const double sx = (s0.x + s1.x) + (s2.x + s3.x), sy = (s0.y + s1.y) + (s2.y + s3.y);
     if (G == 1) {
-        if (g == 0 && pr < pairs) { out[2 * pr] = sx0 + sx1; out[2 * pr + 1] = sy0 + sy1; } // threads past the last full group idle
+        if (g == 0 && pr < pairs) { cl.put(out + 2 * (p0 + pr), sx); cl.put(out + 2 * (p0 + pr) + 1, sy); } // threads past the last full group idle
         return;
     }
     if (g < G && pr < pairs) {
-        part[2 * (g * rp + pr)] = sx0 + sx1;
-        part[2 * (g * rp + pr) + 1] = sy0 + sy1;
+        part[2 * (g * rp + pr)] = sx;
+        part[2 * (g * rp + pr) + 1] = sy;
     }
     __syncthreads();
     if (tid < pairs) {
         double ax = part[2 * tid], ay = part[2 * tid + 1];
         for (int k = 1; k < G; ++k) { ax += part[2 * (k * rp + tid)]; ay += part[2 * (k * rp + tid) + 1]; }
-        out[2 * tid] = ax;
-        out[2 * tid + 1] = ay;
+        cl.put(out + 2 * (p0 + tid), ax);
+        cl.put(out + 2 * (p0 + tid) + 1, ay);
+    }
+}
+
+// Q1[:, c] -= wv * cv[c] for c in [0, ncols): a thread owns a pair of rows, the columns are split over the thread groups and
+// taken four at a time (four independent 128-bit loads in flight, then four stores)
+template <class CL>
+__device__ __forceinline__ void gt_q1_rank1(const CL& cl, const GtWork& W, int ld, int q1s, int ncols, const double* __restrict__ wv,
+    const double* __restrict__ cv)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int all = ld >> 1, per = (all + cl.size() - 1) / cl.size();
+    const int p0 = min(all, cl.rank() * per), pairs = min(all, p0 + per) - p0;
+    const int rp = max(32, round32(pairs));
+    const int G = max(1, T / rp);
+    auto colp = [&](int c) -> double* { return (c < q1s ? W.Q1s : W.Q1) + size_t(c) * ld + 2 * p0; };
+    for (int pr = (T < rp) ? tid : (tid % rp), g = (T < rp) ? 0 : tid / rp; pr < pairs && g < G; pr += (T < rp) ? T : pairs + rp) {
+        const double2 w = *reinterpret_cast<const double2*>(wv + 2 * (p0 + pr));
+        int c = g;
+        for (; c + 3 * G < ncols; c += 4 * G) {
+            double2* p0 = reinterpret_cast<double2*>(colp(c) + 2 * pr);
+            double2* p1 = reinterpret_cast<double2*>(colp(c + G) + 2 * pr);
+            double2* p2 = reinterpret_cast<double2*>(colp(c + 2 * G) + 2 * pr);
+            double2* p3 = reinterpret_cast<double2*>(colp(c + 3 * G) + 2 * pr);
+            double2 a0 = *p0, a1 = *p1, a2 = *p2, a3 = *p3;
+            const double c0 = cv[c], c1 = cv[c + G], c2 = cv[c + 2 * G], c3 = cv[c + 3 * G];
+            a0.x = fma(-w.x, c0, a0.x); a0.y = fma(-w.y, c0, a0.y);
+            a1.x = fma(-w.x, c1, a1.x); a1.y = fma(-w.y, c1, a1.y);
+            a2.x = fma(-w.x, c2, a2.x); a2.y = fma(-w.y, c2, a2.y);
+            a3.x = fma(-w.x, c3, a3.x); a3.y = fma(-w.y, c3, a3.y);
+            *p0 = a0; *p1 = a1; *p2 = a2; *p3 = a3;
+        }
+        for (; c < ncols; c += G) {
+            double2* p0 = reinterpret_cast<double2*>(colp(c) + 2 * pr);
+            double2 a0 = *p0;
+            const double c0 = cv[c];
+            a0.x = fma(-w.x, c0, a0.x); a0.y = fma(-w.y, c0, a0.y);
+            *p0 = a0;
+        }
+    }
+}
+
+// S[rowmap[r], c] -= rv[r] * cv[c] for r in [0, rows) except `skip`, c in [0, ncols): lanes along rows, columns split over
+// thread groups, four at a time
+template <class CL>
+__device__ __forceinline__ void gt_s_rank1(const CL& cl, double* __restrict__ S, size_t lds, const int* __restrict__ rowmap, int rows_all, int skip,
+    int ncols, const double* __restrict__ rv, const double* __restrict__ cv)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int per = (rows_all + cl.size() - 1) / cl.size(), r0 = min(rows_all, cl.rank() * per), rows = min(rows_all, r0 + per) - r0;
+    const int rp = max(32, round32(rows));
+    const int G = max(1, T / rp);
+    rowmap += r0; rv += r0; skip -= r0;
+    for (int r = (T < rp) ? tid : (tid % rp), g = (T < rp) ? 0 : tid / rp; r < rows && g < G; r += (T < rp) ? T : rows + rp) {
+        if (r == skip) continue;
+        double* sr = S + rowmap[r];
+        const double ri = rv[r];
+        int c = g;
+        for (; c + 3 * G < ncols; c += 4 * G) {
+            double a0 = sr[size_t(c) * lds], a1 = sr[size_t(c + G) * lds], a2 = sr[size_t(c + 2 * G) * lds], a3 = sr[size_t(c + 3 * G) * lds];
+            a0 = fma(-ri, cv[c], a0); a1 = fma(-ri, cv[c + G], a1); a2 = fma(-ri, cv[c + 2 * G], a2); a3 = fma(-ri, cv[c + 3 * G], a3);
+            sr[size_t(c) * lds] = a0; sr[size_t(c + G) * lds] = a1; sr[size_t(c + 2 * G) * lds] = a2; sr[size_t(c + 3 * G) * lds] = a3;
+        }
+        for (; c < ncols; c += G) sr[size_t(c) * lds] = fma(-ri, cv[c], sr[size_t(c) * lds]);
     }
 }
 
 // out[r] = sum_{c in [c0,c1)} M[rowof(r) + c*ld] * vec[c], r in [0, rows) -- the S mat-vecs (rows through rowmap).
 // Lanes along rows, the column range split over G = T / round32(rows) thread groups; one __syncthreads when G > 1.
-template <class FR>
-__device__ __forceinline__ void gt_row_dots(const double* __restrict__ M, size_t ld, int rows, int c0, int c1, FR rowof,
-    const double* __restrict__ vec, double* __restrict__ out, double* __restrict__ part)
+template <class CL, class FR>
+__device__ __forceinline__ void gt_row_dots(const CL& cl, const double* __restrict__ M, size_t ld, int rows_all, int c0, int c1, FR rowof_all,
+    const double* __restrict__ vec, double* __restrict__ out_all, double* __restrict__ part)
 {
     const int tid = threadIdx.x, T = blockDim.x;
+    const int per = (rows_all + cl.size() - 1) / cl.size(), r0 = min(rows_all, cl.rank() * per), rows = min(rows_all, r0 + per) - r0;
+    auto rowof = [&](int r) { return rowof_all(r0 + r); };
+    double* out = out_all + r0;
     const int rp = max(32, round32(rows));
     const int G = max(1, T / rp);
     if (G <= 1) {
@@ -332,7 +451,7 @@ __device__ __forceinline__ void gt_row_dots(const double* __restrict__ M, size_t
                 s3 = fma(m3, vec[c + 3], s3);
             }
             for (; c < c1; ++c) s0 = fma(mr[size_t(c) * ld], vec[c], s0);
-            out[r] = (s0 + s1) + (s2 + s3);
+            cl.put(out + r, (s0 + s1) + (s2 + s3));
         }
         return;
     }
@@ -353,7 +472,7 @@ __device__ __forceinline__ void gt_row_dots(const double* __restrict__ M, size_t
     if (tid < rows) {
         double s = part[tid];
         for (int k = 1; k < G; ++k) s += part[k * rp + tid];
-        out[tid] = s;
+        cl.put(out + tid, s);
     }
 }
 
@@ -362,10 +481,11 @@ __device__ __forceinline__ void gt_row_dots(const double* __restrict__ M, size_t
 // One warp per (4 steps x 4 lines) tile: the lanes split the kk = i - j range -- the tables are stored kk-fastest and x is
 // de-interleaved per input (xt[bb N + j]) so that every shared-memory load of a warp is a run of consecutive words -- keep
 // 16 accumulators and meet in a 16-shuffle transpose-reduction; fixed summation order (deterministic).
-__device__ __forceinline__ void gt_products(const GtBatch& B, const GtWork& W)
+template <class CL>
+__device__ __forceinline__ void gt_products(const CL& cl, const GtBatch& B, const GtWork& W)
 {
     const int nu = B.nu, N = B.N, ldk = B.ldk;
-    const int lane = lane_id(), wp = warp_id(), nw = blockDim.x >> 5;
+    const int lane = lane_id(), nw = (blockDim.x >> 5) * cl.size(), wp = warp_id() * cl.size() + cl.rank(); // warps of the whole cluster
     for (int k = threadIdx.x; k < B.n; k += blockDim.x) {
         const int j = k / nu, bb = k - j * nu;
         W.xt[bb * N + j] = W.x[k];
@@ -442,7 +562,7 @@ __device__ __forceinline__ void gt_products(const GtBatch& B, const GtWork& W)
             acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
             if ((lane & 1) == 0) {
                 const int e = lane >> 1, s_ = e >> 2, ll = e & 3;
-                if (ib + s_ < F.i1 && l0 + ll < r) out[(ib + s_ - F.i0) * r + l0 + ll] = acc[0];
+                if (ib + s_ < F.i1 && l0 + ll < r) cl.put(out + (ib + s_ - F.i0) * r + l0 + ll, acc[0]);
             }
         }
         task0 += ntask;
@@ -471,7 +591,8 @@ __device__ __forceinline__ double gt_tab(const GtBatch& B, const double* tab, co
 }
 
 // ---- the solver ----------------------------------------------------------------------------------------------------------
-__device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double vsmall, int max_iter)
+template <class CL>
+__device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, int b, double vsmall, int max_iter)
 {
     const int n = B.n, meq = B.meq, m = B.m, mg = meq + m, q = mg + 2 * n, np = gt_even(n);
     const int tid = threadIdx.x, T = blockDim.x;
@@ -521,6 +642,10 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
 
     int fail = 0, nact = 0, iter0 = 0, iter1 = 0;
     if (B.pd[(long long)b * B.pd_stride] == 0) fail = 2;
+    if (B.prekey && fail != 0) {
+        if (tid == 0) { B.prekey[b] = 0; B.preidx[b] = b; }
+        return fail;
+    }
 #ifdef GT_PROFILE
     long long gt_acc[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
     long long gt_t0 = clock64();
@@ -530,7 +655,7 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
 
     if (fail == 0) {
         // ---- unconstrained minimiser x = Jt Jt' (-c) -------------------------------------------------------------------------
-        gt_trap_mv<false>(JtT, ld, n, n, W.av, W.d, W.part);
+        gt_trap_mv<false>(cl, JtT, ld, n, n, W.av, W.d, W.part);
         // ---- norms of the general rows (the reference's summation order: columns ascending) ---------------------------------
         for (int i = tid; i < mg; i += T) {
             double s = 0.0;
@@ -552,7 +677,7 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
             W.norm[i] = sqrt(s);
         }
         __syncthreads();
-        gt_trap_mv<true>(Jt, ld, n, n, W.d, W.x, W.part);
+        gt_trap_mv<true>(cl, Jt, ld, n, n, W.d, W.x, W.part);
         __syncthreads();
         GT_T(0);
 
@@ -562,17 +687,18 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
             if (iter0 > max_iter) { fail = 3; break; }
             // all slacks; most violated normalised constraint, lowest index on ties
             if (mg > 0) {
-                if (B.structured) gt_products(B, W);
+                if (B.structured) gt_products(cl, B, W);
                 else {
-                    if (meq) gt_row_dots(gAeq, size_t(meq), meq, 0, n, [](int r_) { return size_t(r_); }, W.x, W.sl, W.part);
+                    if (meq) gt_row_dots(cl, gAeq, size_t(meq), meq, 0, n, [](int r_) { return size_t(r_); }, W.x, W.sl, W.part);
                     if (meq && m) __syncthreads();
-                    if (m) gt_row_dots(gAin, size_t(m), m, 0, n, [](int r_) { return size_t(r_); }, W.x, W.sl + meq, W.part);
+                    if (m) gt_row_dots(cl, gAin, size_t(m), m, 0, n, [](int r_) { return size_t(r_); }, W.x, W.sl + meq, W.part);
                 }
             }
             __syncthreads();
             GT_T(1);
             MinIdx best; best.v = 0.0; best.i = -1;
             double best_s = 0.0;
+            int nviol = 0;
             for (int i = tid; i < q; i += T) {
                 double s;
                 if (i < meq) s = double(W.sgn[i]) * (W.sl[i] - W.bv[i]);
@@ -584,6 +710,7 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
                     s = -fabs(s);
                 }
                 if (W.active[i]) s = 0.0;
+                nviol += s < 0.0;
                 if (s < 0.0) {
                     const double nrm = (i < mg) ? W.norm[i] : 1.0;
                     MinIdx c; c.v = s / nrm; c.i = i;
@@ -593,6 +720,11 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
                 }
             }
             const MinIdx sel = block_argmin(best, W.red, W.redi);
+            if (B.prekey) { // prepass: only the difficulty estimate is wanted
+                const double cnt = block_sum(double(nviol), W.red);
+                if (tid == 0) { B.prekey[b] = int(cnt); B.preidx[b] = b; }
+                return 0;
+            }
             if (sel.i < 0) break; // optimal
             const int nvl = sel.i;
             if (best.i == nvl) scal[0] = best_s;
@@ -635,7 +767,7 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
                     }
                 } else {
                     __syncthreads();
-                    gt_trap_mv<false>(JtT, ld, n, supp, W.av, W.d, W.part);
+                    gt_trap_mv<false>(cl, JtT, ld, n, supp, W.av, W.d, W.part);
                 }
             } else {
                 const int j = nvl - mg;
@@ -654,9 +786,9 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
                 // d1 = Q1' d ; zt = d - Q1 d1 (second pass when most of d cancelled: "twice is enough")
                 double dd = dnorm2;
                 if (nact > 0) {
-                    gt_q1_col_dots(W, n, ld, q1s, nact, W.d, W.d1);
+                    gt_q1_col_dots(cl, W, n, ld, q1s, nact, W.d, W.d1);
                     __syncthreads();
-                    gt_q1_row_dots(W, ld, q1s, nact, W.d1, W.w, W.part);
+                    gt_q1_row_dots(cl, W, ld, q1s, nact, W.d1, W.w, W.part);
                     __syncthreads();
                     double acc = 0.0;
                     for (int k = tid; k < n; k += T) { const double v = W.d[k] - W.w[k]; W.zt[k] = v; acc += v * v; }
@@ -665,9 +797,9 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
 #ifdef GT_PROFILE
                         ++gt_reorth;
 #endif
-                        gt_q1_col_dots(W, n, ld, q1s, nact, W.zt, W.v);
+                        gt_q1_col_dots(cl, W, n, ld, q1s, nact, W.zt, W.v);
                         __syncthreads();
-                        gt_q1_row_dots(W, ld, q1s, nact, W.v, W.w, W.part);
+                        gt_q1_row_dots(cl, W, ld, q1s, nact, W.v, W.w, W.part);
                         __syncthreads();
                         acc = 0.0;
                         for (int k = tid; k < n; k += T) { const double v = W.zt[k] - W.w[k]; W.zt[k] = v; acc += v * v; }
@@ -680,9 +812,9 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
                 }
                 GT_T(4);
                 // z = Jt zt ; r = S d1
-                gt_trap_mv<true>(Jt, ld, n, n, W.zt, W.z, W.part);
+                gt_trap_mv<true>(cl, Jt, ld, n, n, W.zt, W.z, W.part);
                 __syncthreads();
-                if (nact > 0) gt_row_dots(S, ldn, nact, 0, nact, [&](int r_) { return size_t(W.rowmap[r_]); }, W.d1, W.r, W.part);
+                if (nact > 0) gt_row_dots(cl, S, ldn, nact, 0, nact, [&](int r_) { return size_t(W.rowmap[r_]); }, W.d1, W.r, W.part);
                 __syncthreads();
                 GT_T(5);
                 MinIdx tc; tc.v = 0.0; tc.i = -1;
@@ -782,14 +914,12 @@ __device__ inline int gt_solve(const GtBatch& B, const GtWork& W, int b, double 
                         __syncthreads();
                         for (int k = tid; k < nact; k += T) W.d1[k] = tau * W.v[k];
                         // Q1 v (all rows of Q1) and S v (active rows), then the two rank-1 updates
-                        gt_q1_row_dots(W, ld, q1s, nact, W.v, W.w, W.part);
+                        gt_q1_row_dots(cl, W, ld, q1s, nact, W.v, W.w, W.part);
                         __syncthreads();
-                        gt_row_dots(S, ldn, nact, 0, nact, [&](int r_) { return size_t(W.rowmap[r_]); }, W.v, W.r, W.part);
+                        gt_row_dots(cl, S, ldn, nact, 0, nact, [&](int r_) { return size_t(W.rowmap[r_]); }, W.v, W.r, W.part);
                         __syncthreads();
-                        tile_rc(n, 0, nact - 1, [&](int r_, int c_) { q1col(c_)[r_] -= W.w[r_] * W.d1[c_]; });
-                        tile_rc(nact, 0, nact - 1, [&](int r_, int c_) {
-                            if (r_ != p) S[W.rowmap[r_] + size_t(c_) * ldn] -= W.r[r_] * W.d1[c_];
-                        });
+                        gt_q1_rank1(cl, W, ld, q1s, nact - 1, W.w, W.d1);
+                        gt_s_rank1(cl, S, ldn, W.rowmap, nact, p, nact - 1, W.r, W.d1);
                         __syncthreads();
                         if (warp_id() == 0) {
                             const int lane = lane_id();
@@ -850,6 +980,9 @@ size_t gt_factor_smem(int n);
 // factor `count` Hessians Q (n x n each): Jt / JtT receive count * n * n doubles, pd count flags
 cudaError_t gt_factor_launch(DArr Q, int n, int ld, int count, double* Jt, double* JtT, int* pd, int sms, cudaStream_t st);
 cudaError_t gt_launch(const GtBatch& B, const GtPlan& plan, cudaStream_t st);
+// order = indices sorted by key, descending (stable); `temp` must hold gt_sort_temp_bytes(count) bytes
+size_t gt_sort_temp_bytes(int count);
+cudaError_t gt_sort_launch(const int* keys, int* keys_sorted, const int* idx, int* order, int count, void* temp, size_t temp_bytes, cudaStream_t st);
 cudaError_t gt_psit_fill_launch(const double* Gs, double* PsiT, int nx, int nu, int N, cudaStream_t st);
 
 } // namespace cb

@@ -3,6 +3,8 @@
 #include "gi_thin.cuh"
 #include "launch.h"
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <algorithm>
 #include <cstdlib>
 
@@ -82,10 +84,11 @@ __global__ void __launch_bounds__(MAXT, MINB) gi_thin_kernel(const __grid_consta
     for (;;) {
         if (threadIdx.x == 0) s_next = atomicAdd(B.counter, 1);
         __syncthreads();
-        const int b = s_next;
+        const int q = s_next;
         __syncthreads();
-        if (b >= B.batch) break;
-        gt_solve(B, W, b, B.vsmall, B.max_iter);
+        if (q >= B.batch) break;
+        const int b = B.order ? B.order[q] : q; // longest-first when a prepass ranked the instances
+        gt_solve(GtSolo(), B, W, b, B.vsmall, B.max_iter);
         __syncthreads();
     }
 }
@@ -137,6 +140,18 @@ template <int MAXT, int MINB> static cudaError_t gt_launch_t(const GtBatch& B, c
     if (e != cudaSuccess) return e;
     gi_thin_kernel<MAXT, MINB><<<plan.grid, plan.threads, plan.smem_bytes, st>>>(B);
     return cudaGetLastError();
+}
+
+size_t gt_sort_temp_bytes(int count)
+{
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, (const int*)nullptr, (int*)nullptr, (const int*)nullptr, (int*)nullptr, count);
+    return bytes;
+}
+
+cudaError_t gt_sort_launch(const int* keys, int* keys_sorted, const int* idx, int* order, int count, void* temp, size_t temp_bytes, cudaStream_t st)
+{
+    return cub::DeviceRadixSort::SortPairsDescending(temp, temp_bytes, keys, keys_sorted, idx, order, count, 0, 32, st);
 }
 
 cudaError_t gt_launch(const GtBatch& B, const GtPlan& plan, cudaStream_t st)
