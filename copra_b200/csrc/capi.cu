@@ -471,8 +471,20 @@ bool plan_thin(copra_b200_handle* h)
     T.ld = gt_even(T.n);
     const char* re = getenv("COPRA_B200_THIN_REORTH");
     T.reorth = re ? atof(re) : 1e-2;
-    const GtShape shape{ T.n, T.meq, T.m, tab, T.ldk, T.ld };
+    // state-space evaluation of the general rows (chunks of 16 steps) when its tables fit next to everything else
+    T.nx = P.nx; T.X = P.X;
+    T.ssL = 16; T.ssC = (P.N + T.ssL - 1) / T.ssL;
+    int eg = 0;
+    for (int k = 0; k < P.nfam; ++k) eg += P.fam[k].rows * ((P.fam[k].hasE ? P.nx : 0) + (P.fam[k].hasG ? P.nu : 0));
+    T.ss_doubles = gt_ss_layout(P.nx, P.nu, P.N, T.ssL, T.ssC, eg).total;
+    T.ss = (P.meq + P.mineq > 0 && !getenv("COPRA_B200_THIN_NO_SS")) ? 1 : 0;
+    if (!T.ss) T.ss_doubles = 0;
+    GtShape shape{ T.n, T.meq, T.m, tab, T.ldk, T.ld, T.ss_doubles };
     h->gtplan = gt_plan(shape, T.batch, sms, h->smem_optin);
+    if (T.ss && !h->gtplan.ok) { // does not fit: convolution form
+        T.ss = 0; T.ss_doubles = 0; shape.ss_doubles = 0;
+        h->gtplan = gt_plan(shape, T.batch, sms, h->smem_optin);
+    }
     if (!h->gtplan.ok) return false;
     T.q1s = h->gtplan.q1s;
     h->use_thin = true;
@@ -515,6 +527,8 @@ int run_gt(copra_b200_handle* h, double* x, int* status, int* iters, int* nact, 
     }
     T.Dpsi = use_dpsi ? dpsi : nullptr;
     T.nx = P.nx; T.X = P.X;
+    T.Phi = DArr{ P.Phi, (long long)P.X * P.nx };
+    T.Gs = DArr{ P.Gs, (long long)P.N * P.nx * P.nu };
     CU(cudaMemsetAsync(counter, 0, 2 * sizeof(int), h->stream));
     for (int k = 0; k < P.nfam; ++k) {
         T.fam[k].EGx = P.fam[k].EGx; T.fam[k].sEGx = P.fam[k].sEGx;

@@ -86,6 +86,11 @@ struct GtBatch {
     // -- nx + nu short column reads instead of a triangular mat-vec over Jt (null: per-instance systems, mat-vec path)
     const double* Dpsi;
     int nx, X;
+    // State-space evaluation of the general rows (gt_products_ss): row (step i, line) of a step-size family is
+    // E s_i + G u_i with s_i = sum_{j<i} A^(i-1-j) B u_j the zero-state response -- O(N (L nu + nx) nx) flops through chunks of
+    // L steps instead of the O(m n / 2) convolution.  Phi / Gs: K1's A^k and A^k B blocks of this instance.
+    int ss, ssL, ssC, ss_doubles;
+    DArr Phi, Gs;
     DArr Jt, JtT;       // R^-1 column-major (entries i <= j of column j) and its transpose (entries j >= i of column i)
     const int* pd;      // 1 = Hessian positive definite, per distinct Hessian
     int pd_stride;      // 0 (shared) or 1
@@ -107,19 +112,20 @@ struct GtBatch {
 };
 
 struct GtLayout {
-    size_t oTab, oX, oXt, oD, oZt, oZ, oAv, oR, oU, oD1, oW, oV, oLb, oUb, oSl, oB, oNorm, oRed, oPart, oQ1; // doubles
+    size_t oTab, oSS, oX, oXt, oD, oZt, oZ, oAv, oR, oU, oD1, oW, oV, oLb, oUb, oSl, oB, oNorm, oRed, oPart, oQ1; // doubles
     size_t oIact, oRowmap, oRedI, oActive, oSgn, bytes;                                                       // bytes
 };
 
 __host__ __device__ inline int gt_even(int n) { return (n + 1) & ~1; }
 
 // `q1s` columns of Q1 (ld doubles each) are placed right after the vectors
-__host__ __device__ inline GtLayout gt_layout(int n, int meq, int m, int tab_doubles, int threads, int q1s)
+__host__ __device__ inline GtLayout gt_layout(int n, int meq, int m, int tab_doubles, int threads, int q1s, int ss_doubles = 0)
 {
     GtLayout L;
     const int mg = gt_even(meq + m), np = gt_even(n);
     size_t o = 0;
     L.oTab = o; o += (size_t(tab_doubles) + 1) & ~size_t(1);
+    L.oSS = o; o += (size_t(ss_doubles) + 1) & ~size_t(1);
     L.oX = o; o += np;
     L.oXt = o; o += np;
     L.oD = o; o += np;
@@ -150,7 +156,7 @@ __host__ __device__ inline GtLayout gt_layout(int n, int meq, int m, int tab_dou
 }
 
 struct GtWork {
-    double *tab, *x, *xt, *d, *zt, *z, *av, *r, *u, *d1, *w, *v, *lb, *ub, *sl, *bv, *norm, *red, *part;
+    double *tab, *ss, *x, *xt, *d, *zt, *z, *av, *r, *u, *d1, *w, *v, *lb, *ub, *sl, *bv, *norm, *red, *part;
     int *iact, *rowmap, *redi;
     unsigned char* active;
     signed char* sgn;
@@ -161,7 +167,7 @@ __device__ inline GtWork gt_carve(const GtLayout& L, unsigned char* smem, double
 {
     GtWork W;
     double* base = reinterpret_cast<double*>(smem);
-    W.tab = base + L.oTab; W.x = base + L.oX; W.xt = base + L.oXt; W.d = base + L.oD; W.zt = base + L.oZt; W.z = base + L.oZ;
+    W.tab = base + L.oTab; W.ss = base + L.oSS; W.x = base + L.oX; W.xt = base + L.oXt; W.d = base + L.oD; W.zt = base + L.oZt; W.z = base + L.oZ;
     W.av = base + L.oAv; W.r = base + L.oR; W.u = base + L.oU; W.d1 = base + L.oD1; W.w = base + L.oW; W.v = base + L.oV;
     W.lb = base + L.oLb; W.ub = base + L.oUb; W.sl = base + L.oSl; W.bv = base + L.oB; W.norm = base + L.oNorm;
     W.red = base + L.oRed; W.part = base + L.oPart;
@@ -569,6 +575,98 @@ __device__ __forceinline__ void gt_products(const CL& cl, const GtBatch& B, cons
     }
 }
 
+// offsets (doubles) inside the state-space area W.ss
+struct GtSS { int oG, oP, oPL, oSt, oSc, oEG, total; };
+__host__ __device__ inline GtSS gt_ss_layout(int nx, int nu, int N, int L, int C, int eg_doubles)
+{
+    GtSS s;
+    int o = 0;
+    s.oG = o; o += L * nx * nu;          // GsL[k][e][bb] = (A^k B)[e, bb], k < L
+    s.oP = o; o += (L + 1) * nx * nx;    // PhiL[t] = A^t (column-major nx x nx), t <= L
+    s.oPL = o; o += C * nx * nx;         // PhiLL[k] = A^(k L), k < C
+    s.oSt = o; o += (N + 1) * nx;        // zero-state response s_i, i = 0..N
+    s.oSc = o; o += C * nx;              // chunk-boundary states s_(c L)
+    s.oEG = o; o += eg_doubles;          // per family: E (r x nx) then G (r x nu)
+    s.total = o;
+    return s;
+}
+
+// sl[row] for every general row through the state-space form (see GtBatch::ss); fixed summation order (deterministic)
+template <class CL>
+__device__ __forceinline__ void gt_products_ss(const CL& cl, const GtBatch& B, const GtWork& W)
+{
+    const int nx = B.nx, nu = B.nu, N = B.N, L = B.ssL, C = B.ssC;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const GtSS o = gt_ss_layout(nx, nu, N, L, C, 0);
+    const double* __restrict__ GsL = W.ss + o.oG;
+    const double* __restrict__ PhiL = W.ss + o.oP;
+    const double* __restrict__ PhiLL = W.ss + o.oPL;
+    double* __restrict__ st = W.ss + o.oSt;
+    double* __restrict__ Sc = W.ss + o.oSc;
+    const double* __restrict__ EG = W.ss + o.oEG;
+    const int nxu = nx * nu, nx2 = nx * nx;
+    // A: response of each chunk to its own inputs, loc(i) = sum_{k < t} A^k B u_(i-1-k), t = i - c L
+    for (int w = tid; w < N * nx; w += T) {
+        const int i1 = w / nx, e = w - i1 * nx; // step i = i1 + 1
+        const int t = i1 % L + 1;
+        const double* g = GsL + e * nu;
+        const double* u = W.x + i1 * nu;
+        double a0 = 0.0, a1 = 0.0;
+        int k = 0;
+        for (; k + 1 < t; k += 2) {
+            for (int bb = 0; bb < nu; ++bb) {
+                a0 = fma(g[k * nxu + bb], u[bb - k * nu], a0);
+                a1 = fma(g[(k + 1) * nxu + bb], u[bb - (k + 1) * nu], a1);
+            }
+        }
+        if (k < t) for (int bb = 0; bb < nu; ++bb) a0 = fma(g[k * nxu + bb], u[bb - k * nu], a0);
+        st[(i1 + 1) * nx + e] = a0 + a1;
+    }
+    if (tid < nx) st[tid] = 0.0;
+    __syncthreads();
+    // B: chunk-boundary states s_(c L) = sum_{c' < c} A^((c-1-c') L) loc(c' L + L)
+    for (int w = tid; w < C * nx; w += T) {
+        const int c = w / nx, e = w - c * nx;
+        double a0 = 0.0;
+        for (int cp = 0; cp < c; ++cp) {
+            const double* Am = PhiLL + (c - 1 - cp) * nx2 + e;
+            const double* le = st + (cp * L + L) * nx;
+            for (int f = 0; f < nx; ++f) a0 = fma(Am[f * nx], le[f], a0);
+        }
+        Sc[w] = a0;
+    }
+    __syncthreads();
+    // C: s_i = loc(i) + A^t s_(c L)
+    for (int w = tid + L * nx; w < N * nx; w += T) {
+        const int i1 = w / nx, e = w - i1 * nx;
+        const int c = i1 / L, t = i1 - c * L + 1;
+        const double* Am = PhiL + t * nx2 + e;
+        const double* sc = Sc + c * nx;
+        double a0 = st[(i1 + 1) * nx + e];
+        for (int f = 0; f < nx; ++f) a0 = fma(Am[f * nx], sc[f], a0);
+        st[(i1 + 1) * nx + e] = a0;
+    }
+    __syncthreads();
+    // D: rows E s_i + G u_i
+    int eg = 0;
+    for (int fi = 0; fi < B.nfam; ++fi) {
+        const GtFam& F = B.fam[fi];
+        const int r = F.rows, cnt = r * (F.i1 - F.i0);
+        const double* Ef = F.E.p ? EG + eg : nullptr;
+        if (F.E.p) eg += r * nx;
+        const double* Gf = F.G.p ? EG + eg : nullptr;
+        if (F.G.p) eg += r * nu;
+        double* out = W.sl + (F.is_eq ? 0 : B.meq) + F.row_off;
+        for (int w = tid; w < cnt; w += T) {
+            const int si = w / r, line = w - si * r, step = F.i0 + si;
+            double a0 = 0.0;
+            if (Ef) for (int e = 0; e < nx; ++e) a0 = fma(Ef[line + e * r], st[step * nx + e], a0);
+            if (Gf && step < N) for (int bb = 0; bb < nu; ++bb) a0 = fma(Gf[line + bb * r], W.x[step * nu + bb], a0);
+            cl.put(out + w, a0);
+        }
+    }
+}
+
 // locate general row `g` (0-based in [eq | ineq]) in the family list: family, step and line
 __device__ __forceinline__ void gt_locate(const GtBatch& B, int g, int& fi, int& step, int& line)
 {
@@ -617,6 +715,30 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
                 const int kk = t / rn, rem = t - kk * rn; // rem = line + rows * bb
                 W.tab[F.tab + size_t(rem) * B.ldk + kk] = src[t];
             }
+        }
+    }
+    if (B.ss) {
+        const int nx = B.nx, nu = B.nu, L = B.ssL, C = B.ssC, Xr = B.X, Nnx = B.N * nx;
+        const GtSS o = gt_ss_layout(nx, nu, B.N, L, C, 0);
+        const double* gPhi = B.Phi.at(b);
+        const double* gGs = B.Gs.at(b);
+        for (int t = tid; t < L * nx * nu; t += T) { // GsL[(k nx + e) nu + bb] = Gs[(k nx + e) + bb N nx]
+            const int bb = t % nu, ke = t / nu;
+            W.ss[o.oG + t] = (ke < Nnx) ? gGs[ke + size_t(bb) * Nnx] : 0.0;
+        }
+        for (int t = tid; t < (L + 1) * nx * nx; t += T) { // PhiL[k][e + f nx] = Phi[(k nx + e) + f X]
+            const int k = t / (nx * nx), rem = t - k * nx * nx, f = rem / nx, e = rem - f * nx;
+            W.ss[o.oP + t] = (k <= B.N) ? gPhi[(k * nx + e) + size_t(f) * Xr] : 0.0;
+        }
+        for (int t = tid; t < C * nx * nx; t += T) {
+            const int k = t / (nx * nx), rem = t - k * nx * nx, f = rem / nx, e = rem - f * nx;
+            W.ss[o.oPL + t] = (k * L <= B.N) ? gPhi[(k * L * nx + e) + size_t(f) * Xr] : 0.0;
+        }
+        int eg = o.oEG;
+        for (int fi = 0; fi < B.nfam; ++fi) {
+            const GtFam& F = B.fam[fi];
+            if (F.E.p) { const double* src = F.E.at(b); for (int t = tid; t < F.rows * nx; t += T) W.ss[eg + t] = src[t]; eg += F.rows * nx; }
+            if (F.G.p) { const double* src = F.G.at(b); for (int t = tid; t < F.rows * nu; t += T) W.ss[eg + t] = src[t]; eg += F.rows * nu; }
         }
     }
     {
@@ -687,7 +809,8 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
             if (iter0 > max_iter) { fail = 3; break; }
             // all slacks; most violated normalised constraint, lowest index on ties
             if (mg > 0) {
-                if (B.structured) gt_products(cl, B, W);
+                if (B.ss) gt_products_ss(cl, B, W);
+                else if (B.structured) gt_products(cl, B, W);
                 else {
                     if (meq) gt_row_dots(cl, gAeq, size_t(meq), meq, 0, n, [](int r_) { return size_t(r_); }, W.x, W.sl, W.part);
                     if (meq && m) __syncthreads();
@@ -974,7 +1097,7 @@ struct GtPlan {
     size_t smem_bytes;
     long long ws_stride; // doubles of global workspace per CTA (Q1 + S)
 };
-struct GtShape { int n, meq, m, tab_doubles, ldk, ld; };
+struct GtShape { int n, meq, m, tab_doubles, ldk, ld, ss_doubles; };
 GtPlan gt_plan(const GtShape& s, int batch, int sms, size_t smem_optin);
 size_t gt_factor_smem(int n);
 // factor `count` Hessians Q (n x n each): Jt / JtT receive count * n * n doubles, pd count flags

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(MAXT, MINB) gi_thin_kernel(const __grid_consta
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_next;
-    const GtLayout L = gt_layout(B.n, B.meq, B.m, B.tab_doubles, blockDim.x, B.q1s);
+    const GtLayout L = gt_layout(B.n, B.meq, B.m, B.tab_doubles, blockDim.x, B.q1s, B.ss_doubles);
     GtWork W = gt_carve(L, smem, B.ws + (long long)blockIdx.x * B.ws_stride, B.n);
     for (;;) {
         if (threadIdx.x == 0) s_next = atomicAdd(B.counter, 1);
@@ -104,7 +104,7 @@ GtPlan gt_plan(const GtShape& sh, int batch, int sms, size_t smem_optin)
     GtPlan p{};
     p.threads = gt_env_int("COPRA_B200_THIN_THREADS", 512);
     if (p.threads != 256 && p.threads != 512 && p.threads != 1024) p.threads = 512;
-    const size_t base = gt_layout(sh.n, sh.meq, sh.m, sh.tab_doubles, p.threads, 0).bytes;
+    const size_t base = gt_layout(sh.n, sh.meq, sh.m, sh.tab_doubles, p.threads, 0, sh.ss_doubles).bytes;
     p.ok = base + 2048 <= smem_optin;
     if (!p.ok) return p;
     // one CTA per SM; whatever shared memory the vectors and tables leave holds the head columns of Q1
@@ -116,7 +116,7 @@ GtPlan gt_plan(const GtShape& sh, int batch, int sms, size_t smem_optin)
     q1s = std::min(q1s, sh.n);
     q1s = std::min(q1s, std::max(0, gt_env_int("COPRA_B200_THIN_Q1S", sh.n)));
     p.q1s = q1s;
-    p.smem_bytes = gt_layout(sh.n, sh.meq, sh.m, sh.tab_doubles, p.threads, q1s).bytes;
+    p.smem_bytes = gt_layout(sh.n, sh.meq, sh.m, sh.tab_doubles, p.threads, q1s, sh.ss_doubles).bytes;
     p.per_sm = per_sm;
     p.grid = std::max(1, std::min(batch, sms * per_sm));
     p.ws_stride = (long long)sh.ld * sh.n + (long long)sh.n * sh.n;
