@@ -63,6 +63,7 @@ struct copra_b200_handle {
     bool factor_valid = false; // the thin solver's R^-1 of the last build is resident (re-solves skip the factorisation)
     bool rows_filled = false;  // Aeq / Aineq of the last build are materialised (the structured solver never reads them)
     bool use_thin = false;     // the last build is solved by the thin kernel (gi_thin.cuh)
+    bool gt_pform = false;     // ... in its shared-factor form (P = Jt Q1 kept, no factor mat-vec per pass)
     const char* solver = "";   // K5+K6 kernel(s) of the last solve
     bool nvtx_open = false;    // an NVTX stage range is open on the calling thread
     GtBatch gt{};
@@ -479,13 +480,17 @@ bool plan_thin(copra_b200_handle* h)
     T.ss_doubles = gt_ss_layout(P.nx, P.nu, P.N, T.ssL, T.ssC, eg).total;
     T.ss = (P.meq + P.mineq > 0 && !getenv("COPRA_B200_THIN_NO_SS")) ? 1 : 0;
     if (!T.ss) T.ss_doubles = 0;
-    GtShape shape{ T.n, T.meq, T.m, tab, T.ldk, T.ld, T.ss_doubles };
+    // batch-invariant system AND Hessian: Dpsi / Hpsi tables and the P form of the pass (see GtBatch)
+    const bool shared_all = P.sQ == 0 && P.A.s == 0 && P.B.s == 0 && !getenv("COPRA_B200_THIN_NO_DPSI");
+    GtShape shape{ T.n, T.meq, T.m, tab, T.ldk, T.ld, T.ss_doubles, (shared_all && !getenv("COPRA_B200_THIN_NO_PFORM")) ? 1 : 0 };
     h->gtplan = gt_plan(shape, T.batch, sms, h->smem_optin);
+    if (shape.pform && T.n > h->gtplan.threads) { shape.pform = 0; h->gtplan = gt_plan(shape, T.batch, sms, h->smem_optin); }
     if (T.ss && !h->gtplan.ok) { // does not fit: convolution form
         T.ss = 0; T.ss_doubles = 0; shape.ss_doubles = 0;
         h->gtplan = gt_plan(shape, T.batch, sms, h->smem_optin);
     }
     if (!h->gtplan.ok) return false;
+    h->gt_pform = shape.pform != 0;
     T.q1s = h->gtplan.q1s;
     h->use_thin = true;
     return true;
@@ -508,10 +513,15 @@ int run_gt(copra_b200_handle* h, double* x, int* status, int* iters, int* nact, 
     if ((rc = ws(h, "counter", 2, &counter))) return rc;
     // batch-invariant system and Hessian: Dpsi = Jt' Psi' once per build (one Toeplitz fill + one DMMA GEMM)
     const bool use_dpsi = P.sQ == 0 && P.A.s == 0 && P.B.s == 0 && !getenv("COPRA_B200_THIN_NO_DPSI");
-    double *psit = nullptr, *dpsi = nullptr;
+    const bool pform = use_dpsi && h->gt_pform;
+    double *psit = nullptr, *dpsi = nullptr, *hpsi = nullptr, *hm = nullptr;
     if (use_dpsi) {
         if ((rc = ws(h, "gt_psit", n * size_t(P.X), &psit))) return rc;
         if ((rc = ws(h, "gt_dpsi", ldj * size_t(P.X), &dpsi))) return rc;
+    }
+    if (pform) {
+        if ((rc = ws(h, "gt_hpsi", ldj * size_t(P.X), &hpsi))) return rc;
+        if ((rc = ws(h, "gt_hm", ldj * n, &hm))) return rc;
     }
     if (!h->factor_valid) {
         cudaError_t e = gt_factor_launch(DArr{ P.Q, P.sQ }, P.nvar, T.ld, int(count), Jt, JtT, pd, sms, h->stream);
@@ -523,9 +533,20 @@ int run_gt(copra_b200_handle* h, double* x, int* status, int* iters, int* nact, 
             h->launches += 1; h->call_launches += 1;
             LAUNCHED(dgemm_dmma_launch(1, P.nvar, P.X, P.nvar, 1.0, Jt, T.ld, 0, psit, P.nvar, 0, 0.0, dpsi, T.ld, 0, 1, h->stream));
         }
+        if (pform) { // Hpsi = Jt Dpsi (= Q^-1 Psi'), H = Jt Jt' (= Q^-1)
+            if (T.ld != P.nvar) {
+                CU(cudaMemsetAsync(hpsi, 0, ldj * size_t(P.X) * sizeof(double), h->stream));
+                CU(cudaMemsetAsync(hm, 0, ldj * n * sizeof(double), h->stream));
+            }
+            LAUNCHED(dgemm_dmma_launch(0, P.nvar, P.X, P.nvar, 1.0, Jt, T.ld, 0, dpsi, T.ld, 0, 0.0, hpsi, T.ld, 0, 1, h->stream));
+            LAUNCHED(dgemm_dmma_launch(0, P.nvar, P.nvar, P.nvar, 1.0, Jt, T.ld, 0, JtT, T.ld, 0, 0.0, hm, T.ld, 0, 1, h->stream));
+        }
         h->factor_valid = true;
     }
     T.Dpsi = use_dpsi ? dpsi : nullptr;
+    T.Hpsi = pform ? hpsi : nullptr;
+    T.Hm = pform ? hm : nullptr;
+    T.Qs = pform ? P.Q : nullptr;
     T.nx = P.nx; T.X = P.X;
     T.Phi = DArr{ P.Phi, (long long)P.X * P.nx };
     T.Gs = DArr{ P.Gs, (long long)P.N * P.nx * P.nu };

@@ -85,6 +85,14 @@ struct GtBatch {
     // and d = Jt' a for the step-size row (family, step, line) is  sum_e E[line,e] Dpsi[:, step nx + e] + sum_b G[line,b] Jt'[:, step nu + b]
     // -- nx + nu short column reads instead of a triangular mat-vec over Jt (null: per-instance systems, mat-vec path)
     const double* Dpsi;
+    // With them H = Jt Jt' (= Q^-1, ld x n) and Hpsi = Jt Dpsi (= H Psi', ld x X), the SHARED-FACTOR FORM of the pass: the
+    // solver stores P = Jt Q1 INSTEAD of Q1 (P' Q P = I) and never touches the factor in the iterations:
+    //   h = Jt d = H a (nx + nu column reads of Hpsi / H)      d1 = Q1' d = P' R' Jt' a = P' a      z = Jt zt = h - P d1
+    //   |zt|^2 = d' zt = a' z      |d|^2 = a' h      ADD: P gains z / |zt|      DROP: the same reflection, applied to P
+    // -- two sweeps over P and one over S per pass, nothing else.  Null: the general form (Q1, z = Jt zt).
+    const double* Hpsi;
+    const double* Hm;
+    const double* Qs;   // the shared Hessian (n x n), only for the rare second orthogonalisation pass (v = P' Q z)
     int nx, X;
     // State-space evaluation of the general rows (gt_products_ss): row (step i, line) of a step-size family is
     // E s_i + G u_i with s_i = sum_{j<i} A^(i-1-j) B u_j the zero-state response -- O(N (L nu + nx) nx) flops through chunks of
@@ -142,13 +150,17 @@ __host__ __device__ inline GtLayout gt_layout(int n, int meq, int m, int tab_dou
     L.oSl = o; o += mg;
     L.oB = o; o += mg;
     L.oNorm = o; o += mg;
-    L.oRed = o; o += 4 * kMaxWarps;
-    L.oPart = o; o += (size_t(2 * (threads / 32) + (n + 63) / 64 + 2) << 6) + 2 * size_t(threads);
+    L.oRed = o; o += 10 * kMaxWarps;
+    {
+        const size_t trap = (size_t(2 * (threads / 32) + (n + 63) / 64 + 2) << 6) + 2 * size_t(threads);
+        const size_t pass = 3 * size_t(threads); // gt_pass_rows: P partials (2T) + S partials (T)
+        L.oPart = o; o += trap > pass ? trap : pass;
+    }
     L.oQ1 = o; o += size_t(q1s) * np;
     size_t b = o * sizeof(double);
     L.oIact = b; b += sizeof(int) * size_t(n);
     L.oRowmap = b; b += sizeof(int) * size_t(n);
-    L.oRedI = b; b += sizeof(int) * kMaxWarps;
+    L.oRedI = b; b += sizeof(int) * 2 * kMaxWarps;
     L.oActive = b; b += size_t(mg + 2 * n);
     L.oSgn = b; b += size_t(meq > 0 ? meq : 1);
     L.bytes = (b + 15) & ~size_t(15);
@@ -482,6 +494,98 @@ __device__ __forceinline__ void gt_row_dots(const CL& cl, const double* __restri
     }
 }
 
+// ---- the pass of the shared-factor form (GtBatch::Hpsi) -----------------------------------------------------------------------
+// outw = P vec (a thread per row PAIR, the column range split over G = T / round32(ld / 2) thread groups; P is stored where the
+// general form keeps Q1) and, when outr != null, outr = S vec over the active rows (lanes along rows, columns split over
+// thread groups); all partial sums meet in `part` in fixed order.  Requires n <= blockDim.x.  ONE __syncthreads inside; the
+// caller syncs before reading.
+__device__ __forceinline__ void gt_pass_rows(const GtWork& W, int ld, int q1s, int nact, const double* __restrict__ vec,
+    double* __restrict__ outw, const double* __restrict__ S, size_t lds, double* __restrict__ outr, double* __restrict__ part)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int pairs = ld >> 1, rp = max(32, round32(pairs)), G = max(1, T / rp);
+    double* partQ = part;
+    double* partS = part + 2 * size_t(T);
+    {
+        const int g = tid / rp, pr = tid - g * rp;
+        double2 q0 = make_double2(0.0, 0.0), q1 = q0, q2 = q0, q3 = q0;
+        if (g < G && pr < pairs) {
+            auto colp = [&](int c) -> const double* { return (c < q1s ? W.Q1s : W.Q1) + size_t(c) * ld + 2 * pr; };
+            int c = g;
+            for (; c + 3 * G < nact; c += 4 * G) {
+                const double2 a0 = *reinterpret_cast<const double2*>(colp(c)), a1 = *reinterpret_cast<const double2*>(colp(c + G));
+                const double2 a2 = *reinterpret_cast<const double2*>(colp(c + 2 * G)), a3 = *reinterpret_cast<const double2*>(colp(c + 3 * G));
+                const double v0 = vec[c], v1 = vec[c + G], v2 = vec[c + 2 * G], v3 = vec[c + 3 * G];
+                q0.x = fma(a0.x, v0, q0.x); q0.y = fma(a0.y, v0, q0.y);
+                q1.x = fma(a1.x, v1, q1.x); q1.y = fma(a1.y, v1, q1.y);
+                q2.x = fma(a2.x, v2, q2.x); q2.y = fma(a2.y, v2, q2.y);
+                q3.x = fma(a3.x, v3, q3.x); q3.y = fma(a3.y, v3, q3.y);
+            }
+            for (; c < nact; c += G) {
+                const double2 a0 = *reinterpret_cast<const double2*>(colp(c));
+                const double v0 = vec[c];
+                q0.x = fma(a0.x, v0, q0.x); q0.y = fma(a0.y, v0, q0.y);
+            }
+            *reinterpret_cast<double2*>(partQ + 2 * (g * rp + pr)) = make_double2((q0.x + q1.x) + (q2.x + q3.x), (q0.y + q1.y) + (q2.y + q3.y));
+        }
+    }
+    const int rs = max(32, round32(nact)), GS = max(1, T / rs);
+    if (outr) {
+        const int g = tid / rs, r_ = tid - g * rs;
+        if (g < GS && r_ < nact) {
+            const double* sr = S + W.rowmap[r_];
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int c = g;
+            for (; c + 3 * GS < nact; c += 4 * GS) {
+                const double m0 = sr[size_t(c) * lds], m1 = sr[size_t(c + GS) * lds], m2 = sr[size_t(c + 2 * GS) * lds], m3 = sr[size_t(c + 3 * GS) * lds];
+                s0 = fma(m0, vec[c], s0); s1 = fma(m1, vec[c + GS], s1); s2 = fma(m2, vec[c + 2 * GS], s2); s3 = fma(m3, vec[c + 3 * GS], s3);
+            }
+            for (; c < nact; c += GS) s0 = fma(sr[size_t(c) * lds], vec[c], s0);
+            partS[g * rs + r_] = (s0 + s1) + (s2 + s3);
+        }
+    }
+    __syncthreads();
+    if (tid < pairs) {
+        double2 a = *reinterpret_cast<const double2*>(partQ + 2 * tid);
+        for (int k = 1; k < G; ++k) {
+            const double2 a1 = *reinterpret_cast<const double2*>(partQ + 2 * (k * rp + tid));
+            a.x += a1.x; a.y += a1.y;
+        }
+        *reinterpret_cast<double2*>(outw + 2 * tid) = a;
+    }
+    if (outr && tid < nact) {
+        double s = partS[tid];
+        for (int k = 1; k < GS; ++k) s += partS[k * rs + tid];
+        outr[tid] = s;
+    }
+}
+
+// Fused block reduction of a pass: four sums and the step-length arg-min behind ONE barrier (every warp finishes the
+// reduction redundantly).  `scr` (5 x kMaxWarps doubles) / `scri` must not be touched by anything else between two barriers.
+struct GtPassRed { double dd, zz, za, dn; MinIdx t1; };
+__device__ __forceinline__ GtPassRed gt_pass_reduce(double dd, double zz, double za, double dn, MinIdx tc, double* scr, int* scri)
+{
+    const int lane = lane_id(), wp = warp_id(), nw = (blockDim.x + 31) >> 5;
+    dd = warp_sum(dd); zz = warp_sum(zz); za = warp_sum(za); dn = warp_sum(dn);
+    tc = warp_argmin(tc);
+    if (lane == 0) {
+        scr[wp] = dd; scr[kMaxWarps + wp] = zz; scr[2 * kMaxWarps + wp] = za; scr[3 * kMaxWarps + wp] = dn;
+        scr[4 * kMaxWarps + wp] = tc.v; scri[wp] = tc.i;
+    }
+    __syncthreads();
+    const bool on = lane < nw;
+    GtPassRed r;
+    r.dd = warp_sum(on ? scr[lane] : 0.0);
+    r.zz = warp_sum(on ? scr[kMaxWarps + lane] : 0.0);
+    r.za = warp_sum(on ? scr[2 * kMaxWarps + lane] : 0.0);
+    r.dn = warp_sum(on ? scr[3 * kMaxWarps + lane] : 0.0);
+    MinIdx t;
+    t.v = on ? scr[4 * kMaxWarps + lane] : 0.0;
+    t.i = on ? scri[lane] : -1;
+    r.t1 = warp_argmin(t);
+    return r;
+}
+
 // ---- structured general rows -------------------------------------------------------------------------------------------
 // sl[row] = sum_{j <= min(i, N-1)} sum_bb T[line, bb, i - j] x[j nu + bb]   for every row (family, step i, line).
 // One warp per (4 steps x 4 lines) tile: the lanes split the kk = i - j range -- the tables are stored kk-fastest and x is
@@ -704,6 +808,7 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
     const double* gAeq = B.Aeq.p ? B.Aeq.at(b) : nullptr;
     const double* gAin = B.Aineq.p ? B.Aineq.at(b) : nullptr;
     auto q1col = [&](int c) -> double* { return (c < q1s ? W.Q1s : W.Q1) + size_t(c) * ld; };
+    const bool pform = B.Hpsi != nullptr; // shared-factor form: z = H a - P d1 (see GtBatch::Hpsi)
 
     // ---- 0. load ----------------------------------------------------------------------------------------------------------
     if (B.structured) {
@@ -858,34 +963,34 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
             // the signed normal a_nvl (quadprog orientation a'x >= b) and d = Jt' a: they do not change at label 55
             int bj = -1, supp = n;
             double bsign = 0.0;
+            int hfi = 0, hstep = 0, hline = 0;
             if (nvl < mg) {
                 const double sg = (nvl < meq) ? double(W.sgn[nvl]) : -1.0;
                 if (B.structured) {
-                    int fi, step, line;
-                    gt_locate(B, nvl, fi, step, line);
-                    const GtFam& F = B.fam[fi];
-                    supp = min(step + 1, B.N) * B.nu;
+                    gt_locate(B, nvl, hfi, hstep, hline);
+                    const GtFam& F = B.fam[hfi];
+                    supp = min(hstep + 1, B.N) * B.nu;
                     for (int k = tid; k < np; k += T) {
                         const int j = k / B.nu, bb = k - j * B.nu;
-                        W.av[k] = (k < supp) ? sg * gt_tab(B, W.tab, F, line, bb, step - j) : 0.0;
+                        W.av[k] = (k < supp) ? sg * gt_tab(B, W.tab, F, hline, bb, hstep - j) : 0.0;
                     }
                 } else if (nvl < meq) {
                     for (int k = tid; k < n; k += T) W.av[k] = sg * gAeq[nvl + size_t(k) * meq];
                 } else {
                     for (int k = tid; k < n; k += T) W.av[k] = sg * gAin[(nvl - meq) + size_t(k) * m];
                 }
-                if (B.structured && B.Dpsi) {
-                    int fi, step, line;
-                    gt_locate(B, nvl, fi, step, line);
-                    const GtFam& F = B.fam[fi];
+                if (pform) {
+                    // d is never formed
+                } else if (B.structured && B.Dpsi) {
+                    const GtFam& F = B.fam[hfi];
                     const double* Ef = F.E.p ? F.E.at(b) : nullptr;
-                    const double* Gf = (F.G.p && step < B.N) ? F.G.at(b) : nullptr;
-                    const double* dp = B.Dpsi + size_t(step) * B.nx * ld;
-                    const double* jp = JtT + size_t(step) * B.nu * ld;
+                    const double* Gf = (F.G.p && hstep < B.N) ? F.G.at(b) : nullptr;
+                    const double* dp = B.Dpsi + size_t(hstep) * B.nx * ld;
+                    const double* jp = JtT + size_t(hstep) * B.nu * ld;
                     for (int k = tid; k < n; k += T) {
                         double acc = 0.0;
-                        if (Ef) for (int e = 0; e < B.nx; ++e) acc = fma(Ef[line + e * F.rows], __ldg(dp + k + size_t(e) * ld), acc);
-                        if (Gf) for (int e = 0; e < B.nu; ++e) acc = fma(Gf[line + e * F.rows], __ldg(jp + k + size_t(e) * ld), acc);
+                        if (Ef) for (int e = 0; e < B.nx; ++e) acc = fma(Ef[hline + e * F.rows], __ldg(dp + k + size_t(e) * ld), acc);
+                        if (Gf) for (int e = 0; e < B.nu; ++e) acc = fma(Gf[hline + e * F.rows], __ldg(jp + k + size_t(e) * ld), acc);
                         W.d[k] = sg * acc;
                     }
                 } else {
@@ -897,17 +1002,108 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
                 if (j < n) { bj = j; bsign = -1.0; }
                 else { bj = j - n; bsign = 1.0; }
                 // d[j] = bsign * Jt[bj, j] (j >= bj): a contiguous run of the transposed factor
-                for (int k = tid; k < n; k += T) W.d[k] = (k >= bj) ? bsign * __ldg(JtT + size_t(bj) * ld + k) : 0.0;
+                if (!pform) for (int k = tid; k < n; k += T) W.d[k] = (k >= bj) ? bsign * __ldg(JtT + size_t(bj) * ld + k) : 0.0;
             }
+            // shared-factor form: h = Jt d = H a into W.z (reloaded at every pass: z overwrites it)
+            auto load_h = [&]() {
+                if (bj >= 0) {
+                    const double* hp = B.Hm + size_t(bj) * ld;
+                    for (int k = tid; k < n; k += T) W.z[k] = bsign * __ldg(hp + k);
+                } else {
+                    const double sg = (nvl < meq) ? double(W.sgn[nvl]) : -1.0;
+                    const GtFam& F = B.fam[hfi];
+                    const double* Ef = F.E.p ? F.E.at(b) : nullptr;
+                    const double* Gf = (F.G.p && hstep < B.N) ? F.G.at(b) : nullptr;
+                    const double* dp = B.Hpsi + size_t(hstep) * B.nx * ld;
+                    const double* jp = B.Hm + size_t(hstep) * B.nu * ld;
+                    for (int k = tid; k < n; k += T) {
+                        double acc = 0.0;
+                        if (Ef) for (int e = 0; e < B.nx; ++e) acc = fma(Ef[hline + e * F.rows], __ldg(dp + k + size_t(e) * ld), acc);
+                        if (Gf) for (int e = 0; e < B.nu; ++e) acc = fma(Gf[hline + e * F.rows], __ldg(jp + k + size_t(e) * ld), acc);
+                        W.z[k] = sg * acc;
+                    }
+                }
+            };
+            if (pform) load_h();
             __syncthreads();
             double dnorm2 = 0.0;
-            for (int k = tid; k < n; k += T) dnorm2 += W.d[k] * W.d[k];
-            dnorm2 = block_sum(dnorm2, W.red);
+            if (!pform) {
+                for (int k = tid; k < n; k += T) dnorm2 += W.d[k] * W.d[k];
+                dnorm2 = block_sum(dnorm2, W.red);
+            }
             GT_T(3);
 
-            for (;;) { // label 55
+            for (int pass = 0;; ++pass) { // label 55
+                double dd, zz = 0.0, za = 0.0;
+                MinIdx t1m;
+                if (pform) {
+                    // ---- shared-factor form: d1 = P' a ; [w, r] = [P, S] d1 ; z = h - w ; |zt|^2 = a'z ; |d|^2 = a'h -----------------
+                    if (pass > 0) { load_h(); __syncthreads(); }
+                    if (nact > 0) {
+                        if (bj >= 0) {
+                            for (int c = tid; c < nact; c += T) W.d1[c] = bsign * q1col(c)[bj];
+                        } else {
+                            gt_q1_col_dots(cl, W, n, ld, q1s, nact, W.av, W.d1);
+                        }
+                        __syncthreads();
+                        gt_pass_rows(W, ld, q1s, nact, W.d1, W.w, S, ldn, W.r, W.part);
+                        __syncthreads();
+                    }
+                    GT_T(4);
+                    auto combine = [&](bool first) -> GtPassRed {
+                        double a_zz = 0.0, a_za = 0.0, a_dn = 0.0;
+                        for (int k = tid; k < n; k += T) {
+                            const double ak = (bj >= 0) ? (k == bj ? bsign : 0.0) : W.av[k];
+                            double zk = W.z[k];
+                            if (first) {
+                                a_dn = fma(ak, zk, a_dn); // W.z still holds h
+                                if (nact > 0) { zk -= W.w[k]; W.z[k] = zk; }
+                            }
+                            a_zz = fma(zk, zk, a_zz); a_za = fma(ak, zk, a_za);
+                        }
+                        MinIdx tc; tc.v = 0.0; tc.i = -1;
+                        for (int i = tid; i < nact; i += T) {
+                            if (W.iact[i] - 1 >= meq && W.r[i] > 0.0) {
+                                MinIdx c; c.v = W.u[i] / W.r[i]; c.i = i;
+                                tc = better(tc, c);
+                            }
+                        }
+                        return gt_pass_reduce(0.0, a_zz, a_za, a_dn, tc, W.red + 4 * kMaxWarps, W.redi + kMaxWarps);
+                    };
+                    GtPassRed pr = combine(true);
+                    const double dn_ = pr.dn;
+                    if (nact > 0 && pr.za < B.reorth * dn_) {
+                        // most of d cancelled: second Gram-Schmidt pass, v = Q1' zt = P' (Q z) ; z -= P v ; d1 += v ; r = S d1 again
+#ifdef GT_PROFILE
+                        ++gt_reorth;
+#endif
+                        __syncthreads();
+                        for (int k = tid; k < n; k += T) {
+                            const double* qr = B.Qs + k;
+                            double s0 = 0.0, s1 = 0.0;
+                            int j = 0;
+                            for (; j + 1 < n; j += 2) { s0 = fma(__ldg(qr + size_t(j) * n), W.z[j], s0); s1 = fma(__ldg(qr + size_t(j + 1) * n), W.z[j + 1], s1); }
+                            if (j < n) s0 = fma(__ldg(qr + size_t(j) * n), W.z[j], s0);
+                            W.zt[k] = s0 + s1;
+                        }
+                        for (int k = n + tid; k < np; k += T) W.zt[k] = 0.0;
+                        __syncthreads();
+                        gt_q1_col_dots(cl, W, n, ld, q1s, nact, W.zt, W.v);
+                        __syncthreads();
+                        gt_pass_rows(W, ld, q1s, nact, W.v, W.w, S, ldn, nullptr, W.part);
+                        __syncthreads();
+                        for (int k = tid; k < n; k += T) W.z[k] -= W.w[k];
+                        for (int k = tid; k < nact; k += T) W.d1[k] += W.v[k];
+                        __syncthreads();
+                        gt_row_dots(cl, S, ldn, nact, 0, nact, [&](int r_) { return size_t(W.rowmap[r_]); }, W.d1, W.r, W.part);
+                        __syncthreads();
+                        pr = combine(false);
+                    }
+                    dd = pr.za; zz = pr.zz; za = pr.za; t1m = pr.t1;
+                    GT_T(5);
+                } else {
                 // d1 = Q1' d ; zt = d - Q1 d1 (second pass when most of d cancelled: "twice is enough")
-                double dd = dnorm2;
+                dd = dnorm2;
                 if (nact > 0) {
                     gt_q1_col_dots(cl, W, n, ld, q1s, nact, W.d, W.d1);
                     __syncthreads();
@@ -947,18 +1143,18 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
                         tc = better(tc, c);
                     }
                 }
-                const MinIdx t1m = block_argmin(tc, W.red, W.redi);
-                const bool t1inf = t1m.i < 0;
-                const double t1 = t1m.v;
-                const int it1 = t1m.i;
-                double zz = 0.0, za = 0.0;
+                t1m = block_argmin(tc, W.red, W.redi);
                 for (int j = tid; j < n; j += T) {
                     const double zj = W.z[j];
                     zz += zj * zj;
                     if (bj < 0) za += zj * W.av[j];
                 }
                 block_sum2(zz, za, W.red);
-                if (bj >= 0) za = bsign * W.z[bj];
+                }
+                const bool t1inf = t1m.i < 0;
+                const double t1 = t1m.v;
+                const int it1 = t1m.i;
+                if (bj >= 0 && !pform) za = bsign * W.z[bj];
 
                 bool do_drop = false;
                 if (fabs(zz) <= vsmall) {
@@ -977,7 +1173,8 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
                         // ---- add constraint nvl: Q1 gains zt / delta, S the column [-r/delta ; 1/delta] ----------------------
                         const double delta = sqrt(dd), inv = 1.0 / delta;
                         double* qc = q1col(nact);
-                        for (int j = tid; j < np; j += T) qc[j] = (j < n) ? W.zt[j] * inv : 0.0;
+                        const double* src = pform ? W.z : W.zt; // shared-factor form: the column of P = Jt Q1 is z / |zt|
+                        for (int j = tid; j < np; j += T) qc[j] = (j < n) ? src[j] * inv : 0.0;
                         const int newrow = W.rowmap[nact];
                         for (int i = tid; i < nact; i += T) {
                             S[W.rowmap[i] + size_t(nact) * ldn] = -W.r[i] * inv;
@@ -1037,10 +1234,15 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
                         __syncthreads();
                         for (int k = tid; k < nact; k += T) W.d1[k] = tau * W.v[k];
                         // Q1 v (all rows of Q1) and S v (active rows), then the two rank-1 updates
-                        gt_q1_row_dots(cl, W, ld, q1s, nact, W.v, W.w, W.part);
-                        __syncthreads();
-                        gt_row_dots(cl, S, ldn, nact, 0, nact, [&](int r_) { return size_t(W.rowmap[r_]); }, W.v, W.r, W.part);
-                        __syncthreads();
+                        if (pform) {
+                            gt_pass_rows(W, ld, q1s, nact, W.v, W.w, S, ldn, W.r, W.part);
+                            __syncthreads();
+                        } else {
+                            gt_q1_row_dots(cl, W, ld, q1s, nact, W.v, W.w, W.part);
+                            __syncthreads();
+                            gt_row_dots(cl, S, ldn, nact, 0, nact, [&](int r_) { return size_t(W.rowmap[r_]); }, W.v, W.r, W.part);
+                            __syncthreads();
+                        }
                         gt_q1_rank1(cl, W, ld, q1s, nact - 1, W.w, W.d1);
                         gt_s_rank1(cl, S, ldn, W.rowmap, nact, p, nact - 1, W.r, W.d1);
                         __syncthreads();
@@ -1097,7 +1299,7 @@ struct GtPlan {
     size_t smem_bytes;
     long long ws_stride; // doubles of global workspace per CTA (Q1 + S)
 };
-struct GtShape { int n, meq, m, tab_doubles, ldk, ld, ss_doubles; };
+struct GtShape { int n, meq, m, tab_doubles, ldk, ld, ss_doubles, pform; };
 GtPlan gt_plan(const GtShape& s, int batch, int sms, size_t smem_optin);
 size_t gt_factor_smem(int n);
 // factor `count` Hessians Q (n x n each): Jt / JtT receive count * n * n doubles, pd count flags
