@@ -491,6 +491,8 @@ bool plan_thin(copra_b200_handle* h)
     }
     if (!h->gtplan.ok) return false;
     h->gt_pform = shape.pform != 0;
+    T.lay = gt_layout(T.n, T.meq, T.m, T.tab_doubles, h->gtplan.threads, h->gtplan.q1s, T.ss_doubles);
+    T.ssl = gt_ss_layout(P.nx, P.nu, P.N, T.ssL, T.ssC, eg);
     T.q1s = h->gtplan.q1s;
     h->use_thin = true;
     return true;

@@ -65,6 +65,14 @@ struct GtClus {
     }
 };
 
+struct GtLayout {
+    size_t oTab, oSS, oX, oXt, oD, oZt, oZ, oAv, oR, oU, oD1, oW, oV, oLb, oUb, oSl, oB, oNorm, oRed, oPart, oQ1; // doubles
+    size_t oIact, oRowmap, oRedI, oActive, oSgn, bytes;                                                       // bytes
+};
+
+// offsets (doubles) inside the state-space area W.ss
+struct GtSS { int oG, oP, oPL, oSt, oSc, oEG, total; };
+
 struct GtFam {
     int rows, i0, i1, is_eq, row_off; // row_off: first row inside Aeq (is_eq) or Aineq
     int tab;                          // offset of this family's table in the shared-memory table area (doubles)
@@ -99,6 +107,10 @@ struct GtBatch {
     // L steps instead of the O(m n / 2) convolution.  Phi / Gs: K1's A^k and A^k B blocks of this instance.
     int ss, ssL, ssC, ss_doubles;
     DArr Phi, Gs;
+    // shared-memory layout, computed ONCE on the host (gt_layout / gt_ss_layout with the launch's thread count): the kernel reads
+    // the offsets from the constant bank instead of re-deriving them wherever a pointer is re-materialised
+    GtLayout lay;
+    GtSS ssl;
     DArr Jt, JtT;       // R^-1 column-major (entries i <= j of column j) and its transpose (entries j >= i of column i)
     const int* pd;      // 1 = Hessian positive definite, per distinct Hessian
     int pd_stride;      // 0 (shared) or 1
@@ -117,11 +129,6 @@ struct GtBatch {
     int* prekey;
     int* preidx;
     const int* order;
-};
-
-struct GtLayout {
-    size_t oTab, oSS, oX, oXt, oD, oZt, oZ, oAv, oR, oU, oD1, oW, oV, oLb, oUb, oSl, oB, oNorm, oRed, oPart, oQ1; // doubles
-    size_t oIact, oRowmap, oRedI, oActive, oSgn, bytes;                                                       // bytes
 };
 
 __host__ __device__ inline int gt_even(int n) { return (n + 1) & ~1; }
@@ -510,20 +517,28 @@ __device__ __forceinline__ void gt_pass_rows(const GtWork& W, int ld, int q1s, i
         const int g = tid / rp, pr = tid - g * rp;
         double2 q0 = make_double2(0.0, 0.0), q1 = q0, q2 = q0, q3 = q0;
         if (g < G && pr < pairs) {
-            auto colp = [&](int c) -> const double* { return (c < q1s ? W.Q1s : W.Q1) + size_t(c) * ld + 2 * pr; };
             int c = g;
-            for (; c + 3 * G < nact; c += 4 * G) {
-                const double2 a0 = *reinterpret_cast<const double2*>(colp(c)), a1 = *reinterpret_cast<const double2*>(colp(c + G));
-                const double2 a2 = *reinterpret_cast<const double2*>(colp(c + 2 * G)), a3 = *reinterpret_cast<const double2*>(colp(c + 3 * G));
-                const double v0 = vec[c], v1 = vec[c + G], v2 = vec[c + 2 * G], v3 = vec[c + 3 * G];
+            // head columns (shared memory), then the global workspace: plain pointer walks, four loads in flight
+            for (; c < min(q1s, nact); c += G) {
+                const double2 a0 = *reinterpret_cast<const double2*>(W.Q1s + size_t(c) * ld + 2 * pr);
+                const double v0 = vec[c];
+                q0.x = fma(a0.x, v0, q0.x); q0.y = fma(a0.y, v0, q0.y);
+            }
+            const size_t cs = size_t(G) * ld;
+            const double* cp = W.Q1 + size_t(c) * ld + 2 * pr;
+            const double* vp = vec + c;
+            for (; c + 3 * G < nact; c += 4 * G, cp += 4 * cs, vp += 4 * G) {
+                const double2 a0 = *reinterpret_cast<const double2*>(cp), a1 = *reinterpret_cast<const double2*>(cp + cs);
+                const double2 a2 = *reinterpret_cast<const double2*>(cp + 2 * cs), a3 = *reinterpret_cast<const double2*>(cp + 3 * cs);
+                const double v0 = vp[0], v1 = vp[G], v2 = vp[2 * G], v3 = vp[3 * G];
                 q0.x = fma(a0.x, v0, q0.x); q0.y = fma(a0.y, v0, q0.y);
                 q1.x = fma(a1.x, v1, q1.x); q1.y = fma(a1.y, v1, q1.y);
                 q2.x = fma(a2.x, v2, q2.x); q2.y = fma(a2.y, v2, q2.y);
                 q3.x = fma(a3.x, v3, q3.x); q3.y = fma(a3.y, v3, q3.y);
             }
-            for (; c < nact; c += G) {
-                const double2 a0 = *reinterpret_cast<const double2*>(colp(c));
-                const double v0 = vec[c];
+            for (; c < nact; c += G, cp += cs, vp += G) {
+                const double2 a0 = *reinterpret_cast<const double2*>(cp);
+                const double v0 = vp[0];
                 q0.x = fma(a0.x, v0, q0.x); q0.y = fma(a0.y, v0, q0.y);
             }
             *reinterpret_cast<double2*>(partQ + 2 * (g * rp + pr)) = make_double2((q0.x + q1.x) + (q2.x + q3.x), (q0.y + q1.y) + (q2.y + q3.y));
@@ -533,14 +548,16 @@ __device__ __forceinline__ void gt_pass_rows(const GtWork& W, int ld, int q1s, i
     if (outr) {
         const int g = tid / rs, r_ = tid - g * rs;
         if (g < GS && r_ < nact) {
-            const double* sr = S + W.rowmap[r_];
+            const size_t cs = size_t(GS) * lds;
+            const double* sr = S + W.rowmap[r_] + size_t(g) * lds;
+            const double* vp = vec + g;
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
             int c = g;
-            for (; c + 3 * GS < nact; c += 4 * GS) {
-                const double m0 = sr[size_t(c) * lds], m1 = sr[size_t(c + GS) * lds], m2 = sr[size_t(c + 2 * GS) * lds], m3 = sr[size_t(c + 3 * GS) * lds];
-                s0 = fma(m0, vec[c], s0); s1 = fma(m1, vec[c + GS], s1); s2 = fma(m2, vec[c + 2 * GS], s2); s3 = fma(m3, vec[c + 3 * GS], s3);
+            for (; c + 3 * GS < nact; c += 4 * GS, sr += 4 * cs, vp += 4 * GS) {
+                const double m0 = sr[0], m1 = sr[cs], m2 = sr[2 * cs], m3 = sr[3 * cs];
+                s0 = fma(m0, vp[0], s0); s1 = fma(m1, vp[GS], s1); s2 = fma(m2, vp[2 * GS], s2); s3 = fma(m3, vp[3 * GS], s3);
             }
-            for (; c < nact; c += GS) s0 = fma(sr[size_t(c) * lds], vec[c], s0);
+            for (; c < nact; c += GS, sr += cs, vp += GS) s0 = fma(sr[0], vp[0], s0);
             partS[g * rs + r_] = (s0 + s1) + (s2 + s3);
         }
     }
@@ -679,8 +696,6 @@ __device__ __forceinline__ void gt_products(const CL& cl, const GtBatch& B, cons
     }
 }
 
-// offsets (doubles) inside the state-space area W.ss
-struct GtSS { int oG, oP, oPL, oSt, oSc, oEG, total; };
 __host__ __device__ inline GtSS gt_ss_layout(int nx, int nu, int N, int L, int C, int eg_doubles)
 {
     GtSS s;
@@ -695,13 +710,44 @@ __host__ __device__ inline GtSS gt_ss_layout(int nx, int nu, int N, int L, int C
     return s;
 }
 
+// phase A of gt_products_ss for a compile-time input count (0: run-time `nu_rt`): the inner products unroll and the lag loop
+// advances two pointers
+template <int NU>
+__device__ __forceinline__ void gt_ss_local(const double* __restrict__ GsL, const double* __restrict__ x, double* __restrict__ st,
+    int nx, int N, int L, int nu_rt = 0)
+{
+    const int nu = NU ? NU : nu_rt;
+    const int nxu = nx * nu;
+    // thread -> (step, state row): consecutive threads take consecutive rows of one step
+    int i1 = threadIdx.x / nx, e = threadIdx.x - i1 * nx;
+    const int di = blockDim.x / nx, de = blockDim.x - di * nx;
+    for (; i1 < N;) {
+        const int t = i1 % L + 1;
+        const double* g = GsL + e * nu;
+        const double* u = x + i1 * nu;
+        double a0 = 0.0, a1 = 0.0;
+        int k = 0;
+        for (; k + 1 < t; k += 2, g += 2 * nxu, u -= 2 * nu) {
+#pragma unroll
+            for (int bb = 0; bb < (NU ? NU : 1); ++bb) {
+                if (NU) { a0 = fma(g[bb], u[bb], a0); a1 = fma(g[nxu + bb], u[bb - nu], a1); }
+            }
+            if (!NU) for (int bb = 0; bb < nu; ++bb) { a0 = fma(g[bb], u[bb], a0); a1 = fma(g[nxu + bb], u[bb - nu], a1); }
+        }
+        if (k < t) for (int bb = 0; bb < nu; ++bb) a0 = fma(g[bb], u[bb], a0);
+        st[(i1 + 1) * nx + e] = a0 + a1;
+        i1 += di; e += de;
+        if (e >= nx) { e -= nx; ++i1; }
+    }
+}
+
 // sl[row] for every general row through the state-space form (see GtBatch::ss); fixed summation order (deterministic)
 template <class CL>
 __device__ __forceinline__ void gt_products_ss(const CL& cl, const GtBatch& B, const GtWork& W)
 {
     const int nx = B.nx, nu = B.nu, N = B.N, L = B.ssL, C = B.ssC;
     const int tid = threadIdx.x, T = blockDim.x;
-    const GtSS o = gt_ss_layout(nx, nu, N, L, C, 0);
+    const GtSS& o = B.ssl;
     const double* __restrict__ GsL = W.ss + o.oG;
     const double* __restrict__ PhiL = W.ss + o.oP;
     const double* __restrict__ PhiLL = W.ss + o.oPL;
@@ -710,21 +756,11 @@ __device__ __forceinline__ void gt_products_ss(const CL& cl, const GtBatch& B, c
     const double* __restrict__ EG = W.ss + o.oEG;
     const int nxu = nx * nu, nx2 = nx * nx;
     // A: response of each chunk to its own inputs, loc(i) = sum_{k < t} A^k B u_(i-1-k), t = i - c L
-    for (int w = tid; w < N * nx; w += T) {
-        const int i1 = w / nx, e = w - i1 * nx; // step i = i1 + 1
-        const int t = i1 % L + 1;
-        const double* g = GsL + e * nu;
-        const double* u = W.x + i1 * nu;
-        double a0 = 0.0, a1 = 0.0;
-        int k = 0;
-        for (; k + 1 < t; k += 2) {
-            for (int bb = 0; bb < nu; ++bb) {
-                a0 = fma(g[k * nxu + bb], u[bb - k * nu], a0);
-                a1 = fma(g[(k + 1) * nxu + bb], u[bb - (k + 1) * nu], a1);
-            }
-        }
-        if (k < t) for (int bb = 0; bb < nu; ++bb) a0 = fma(g[k * nxu + bb], u[bb - k * nu], a0);
-        st[(i1 + 1) * nx + e] = a0 + a1;
+    switch (nu) {
+    case 1: gt_ss_local<1>(GsL, W.x, st, nx, N, L); break;
+    case 2: gt_ss_local<2>(GsL, W.x, st, nx, N, L); break;
+    case 4: gt_ss_local<4>(GsL, W.x, st, nx, N, L); break;
+    default: gt_ss_local<0>(GsL, W.x, st, nx, N, L, nu); break;
     }
     if (tid < nx) st[tid] = 0.0;
     __syncthreads();
@@ -743,7 +779,7 @@ __device__ __forceinline__ void gt_products_ss(const CL& cl, const GtBatch& B, c
     // C: s_i = loc(i) + A^t s_(c L)
     for (int w = tid + L * nx; w < N * nx; w += T) {
         const int i1 = w / nx, e = w - i1 * nx;
-        const int c = i1 / L, t = i1 - c * L + 1;
+        const int c = i1 / L, t = i1 - c * L + 1; // L is a power of two on the host side
         const double* Am = PhiL + t * nx2 + e;
         const double* sc = Sc + c * nx;
         double a0 = st[(i1 + 1) * nx + e];
@@ -824,7 +860,7 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
     }
     if (B.ss) {
         const int nx = B.nx, nu = B.nu, L = B.ssL, C = B.ssC, Xr = B.X, Nnx = B.N * nx;
-        const GtSS o = gt_ss_layout(nx, nu, B.N, L, C, 0);
+        const GtSS& o = B.ssl;
         const double* gPhi = B.Phi.at(b);
         const double* gGs = B.Gs.at(b);
         for (int t = tid; t < L * nx * nu; t += T) { // GsL[(k nx + e) nu + bb] = Gs[(k nx + e) + bb N nx]

@@ -79,8 +79,7 @@ __global__ void __launch_bounds__(MAXT, MINB) gi_thin_kernel(const __grid_consta
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_next;
-    const GtLayout L = gt_layout(B.n, B.meq, B.m, B.tab_doubles, blockDim.x, B.q1s, B.ss_doubles);
-    GtWork W = gt_carve(L, smem, B.ws + (long long)blockIdx.x * B.ws_stride, B.n);
+    GtWork W = gt_carve(B.lay, smem, B.ws + (long long)blockIdx.x * B.ws_stride, B.n);
     for (;;) {
         if (threadIdx.x == 0) s_next = atomicAdd(B.counter, 1);
         __syncthreads();
