@@ -489,6 +489,18 @@ bool plan_thin(copra_b200_handle* h)
         T.ss = 0; T.ss_doubles = 0; shape.ss_doubles = 0;
         h->gtplan = gt_plan(shape, T.batch, sms, h->smem_optin);
     }
+    // Per-instance factors and big streams (n >= 512) in a batch of only a few waves: the step is the latency of its heaviest
+    // instance, which is bound by what ONE SM can stream -- give every instance a thread-block cluster instead.
+    {
+        const char* ce = getenv("COPRA_B200_THIN_CLUSTER");
+        int csize = ce ? atoi(ce) : ((!shared_all && P.sQ != 0 && T.n >= 512 && P.batch <= 16 * sms) ? 8 : 0);
+        if (csize > 1 && (csize & (csize - 1)) == 0 && csize <= 8 && h->gtplan.ok) {
+            GtShape cs = shape;
+            cs.cluster = csize; cs.pform = 0; cs.ss_doubles = 0;
+            const GtPlan cp = gt_plan(cs, T.batch, sms, h->smem_optin);
+            if (cp.ok) { h->gtplan = cp; shape = cs; T.ss = 0; T.ss_doubles = 0; }
+        }
+    }
     if (!h->gtplan.ok) return false;
     h->gt_pform = shape.pform != 0;
     T.lay = gt_layout(T.n, T.meq, T.m, T.tab_doubles, h->gtplan.threads, h->gtplan.q1s, T.ss_doubles);
@@ -577,7 +589,9 @@ int run_gt(copra_b200_handle* h, double* x, int* status, int* iters, int* nact, 
     // few waves of instances per resident CTA: the step ends with the slowest instance, so rank the instances by the number
     // of constraints violated at their unconstrained minimiser (one cheap prepass) and start the heaviest first
     T.prekey = nullptr; T.preidx = nullptr; T.order = nullptr;
-    const bool lpt = P.batch > plan.grid && P.batch <= 24 * plan.grid && !getenv("COPRA_B200_THIN_NO_LPT");
+    T.kheavy = P.batch;
+    const int slots = plan.cluster > 1 ? plan.grid / plan.cluster : plan.grid; // instances in flight
+    const bool lpt = P.batch > slots && (P.batch <= 24 * slots || plan.cluster > 1) && !getenv("COPRA_B200_THIN_NO_LPT");
     cudaError_t e;
     if (lpt) {
         int *keys = nullptr, *keys2 = nullptr, *idx = nullptr, *order = nullptr;
@@ -594,6 +608,8 @@ int run_gt(copra_b200_handle* h, double* x, int* status, int* iters, int* nact, 
         h->launches += 2; h->call_launches += 2;
         CU(cudaMemsetAsync(counter, 0, 2 * sizeof(int), h->stream));
         T.prekey = nullptr; T.preidx = nullptr; T.order = order;
+        // clusters for the head of the longest-first queue only (the heavy tail of the iteration counts)
+        if (plan.cluster > 1) { const char* kh = getenv("COPRA_B200_THIN_HEAVY"); T.kheavy = kh ? atoi(kh) : std::max(1, P.batch / 16); }
     }
     e = gt_launch(T, plan, h->stream);
     if (e != cudaSuccess) return fail(h, COPRA_B200_E_CUDA, "gt_launch: %s", cudaGetErrorString(e));

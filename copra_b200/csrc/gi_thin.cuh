@@ -54,14 +54,14 @@ struct GtSolo {
 };
 struct GtClus {
     static constexpr bool multi = true;
-    cg::cluster_group cl;
     int r, c;
     __device__ __forceinline__ int rank() const { return r; }
     __device__ __forceinline__ int size() const { return c; }
-    __device__ __forceinline__ void sync() const { cl.sync(); }
+    __device__ __forceinline__ void sync() const { cg::this_cluster().sync(); }
     template <class T> __device__ __forceinline__ void put(T* p, T v) const
     {
-        for (int k = 0; k < c; ++k) *cl.map_shared_rank(p, k) = v;
+        cg::cluster_group g = cg::this_cluster();
+        for (int k = 0; k < c; ++k) *g.map_shared_rank(p, k) = v;
     }
 };
 
@@ -129,6 +129,7 @@ struct GtBatch {
     int* prekey;
     int* preidx;
     const int* order;
+    int kheavy; // cluster kernel: queue entries [0, kheavy) are solved by whole clusters, the rest by single CTAs
 };
 
 __host__ __device__ inline int gt_even(int n) { return (n + 1) & ~1; }
@@ -901,12 +902,12 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
         for (int i = tid; i < q; i += T) W.active[i] = 0;
         for (int i = tid; i < meq; i += T) W.sgn[i] = 1;
     }
-    __syncthreads();
+    cl.sync(); // (cluster: no remote store may land before every replica is initialised)
 
     int fail = 0, nact = 0, iter0 = 0, iter1 = 0;
     if (B.pd[(long long)b * B.pd_stride] == 0) fail = 2;
     if (B.prekey && fail != 0) {
-        if (tid == 0) { B.prekey[b] = 0; B.preidx[b] = b; }
+        if (tid == 0 && cl.rank() == 0) { B.prekey[b] = 0; B.preidx[b] = b; }
         return fail;
     }
 #ifdef GT_PROFILE
@@ -939,9 +940,9 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
             }
             W.norm[i] = sqrt(s);
         }
-        __syncthreads();
+        cl.sync();
         gt_trap_mv<true>(cl, Jt, ld, n, n, W.d, W.x, W.part);
-        __syncthreads();
+        cl.sync();
         GT_T(0);
 
         // ---- dual active-set iterations ----------------------------------------------------------------------------------------
@@ -958,7 +959,7 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
                     if (m) gt_row_dots(cl, gAin, size_t(m), m, 0, n, [](int r_) { return size_t(r_); }, W.x, W.sl + meq, W.part);
                 }
             }
-            __syncthreads();
+            cl.sync();
             GT_T(1);
             MinIdx best; best.v = 0.0; best.i = -1;
             double best_s = 0.0;
@@ -986,7 +987,7 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
             const MinIdx sel = block_argmin(best, W.red, W.redi);
             if (B.prekey) { // prepass: only the difficulty estimate is wanted
                 const double cnt = block_sum(double(nviol), W.red);
-                if (tid == 0) { B.prekey[b] = int(cnt); B.preidx[b] = b; }
+                if (tid == 0 && cl.rank() == 0) { B.prekey[b] = int(cnt); B.preidx[b] = b; }
                 return 0;
             }
             if (sel.i < 0) break; // optimal
@@ -1061,7 +1062,7 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
                 }
             };
             if (pform) load_h();
-            __syncthreads();
+            cl.sync();
             double dnorm2 = 0.0;
             if (!pform) {
                 for (int k = tid; k < n; k += T) dnorm2 += W.d[k] * W.d[k];
@@ -1142,9 +1143,9 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
                 dd = dnorm2;
                 if (nact > 0) {
                     gt_q1_col_dots(cl, W, n, ld, q1s, nact, W.d, W.d1);
-                    __syncthreads();
+                    cl.sync();
                     gt_q1_row_dots(cl, W, ld, q1s, nact, W.d1, W.w, W.part);
-                    __syncthreads();
+                    cl.sync();
                     double acc = 0.0;
                     for (int k = tid; k < n; k += T) { const double v = W.d[k] - W.w[k]; W.zt[k] = v; acc += v * v; }
                     dd = block_sum(acc, W.red);
@@ -1153,9 +1154,9 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
                         ++gt_reorth;
 #endif
                         gt_q1_col_dots(cl, W, n, ld, q1s, nact, W.zt, W.v);
-                        __syncthreads();
+                        cl.sync();
                         gt_q1_row_dots(cl, W, ld, q1s, nact, W.v, W.w, W.part);
-                        __syncthreads();
+                        cl.sync();
                         acc = 0.0;
                         for (int k = tid; k < n; k += T) { const double v = W.zt[k] - W.w[k]; W.zt[k] = v; acc += v * v; }
                         for (int k = tid; k < nact; k += T) W.d1[k] += W.v[k];
@@ -1168,9 +1169,9 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
                 GT_T(4);
                 // z = Jt zt ; r = S d1
                 gt_trap_mv<true>(cl, Jt, ld, n, n, W.zt, W.z, W.part);
-                __syncthreads();
+                __syncthreads(); // `part` is reused; z and r are published by the one cluster barrier below
                 if (nact > 0) gt_row_dots(cl, S, ldn, nact, 0, nact, [&](int r_) { return size_t(W.rowmap[r_]); }, W.d1, W.r, W.part);
-                __syncthreads();
+                cl.sync();
                 GT_T(5);
                 MinIdx tc; tc.v = 0.0; tc.i = -1;
                 for (int i = tid; i < nact; i += T) {
@@ -1210,19 +1211,21 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
                         const double delta = sqrt(dd), inv = 1.0 / delta;
                         double* qc = q1col(nact);
                         const double* src = pform ? W.z : W.zt; // shared-factor form: the column of P = Jt Q1 is z / |zt|
-                        for (int j = tid; j < np; j += T) qc[j] = (j < n) ? src[j] * inv : 0.0;
+                        for (int j = tid * cl.size() + cl.rank(); j < np; j += T * cl.size()) qc[j] = (j < n) ? src[j] * inv : 0.0;
                         const int newrow = W.rowmap[nact];
-                        for (int i = tid; i < nact; i += T) {
-                            S[W.rowmap[i] + size_t(nact) * ldn] = -W.r[i] * inv;
-                            S[newrow + size_t(i) * ldn] = 0.0;
+                        if (cl.rank() == 0) {
+                            for (int i = tid; i < nact; i += T) {
+                                S[W.rowmap[i] + size_t(nact) * ldn] = -W.r[i] * inv;
+                                S[newrow + size_t(i) * ldn] = 0.0;
+                            }
+                            if (tid == 0) S[newrow + size_t(nact) * ldn] = inv;
                         }
                         if (tid == 0) {
-                            S[newrow + size_t(nact) * ldn] = inv;
                             W.iact[nact] = nvl + 1;
                             W.active[nvl] = 1;
                         }
                         ++nact;
-                        __syncthreads();
+                        cl.sync();
                         GT_T(6);
                         break; // next outer iteration
                     } else {
@@ -1253,7 +1256,7 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
                 }
                 if (do_drop) {
                     // ---- drop the it1-th active constraint: reflection with last column ~ row p of S ---------------------------
-                    __syncthreads();
+                    cl.sync(); // (cluster: every replica has finished reading r / w before the stores below replace them)
                     const int p = it1;
                     const int dropped = (tid == 0) ? W.iact[p] - 1 : 0;
                     const int prow = W.rowmap[p];
@@ -1277,11 +1280,11 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
                             gt_q1_row_dots(cl, W, ld, q1s, nact, W.v, W.w, W.part);
                             __syncthreads();
                             gt_row_dots(cl, S, ldn, nact, 0, nact, [&](int r_) { return size_t(W.rowmap[r_]); }, W.v, W.r, W.part);
-                            __syncthreads();
+                            cl.sync();
                         }
                         gt_q1_rank1(cl, W, ld, q1s, nact - 1, W.w, W.d1);
                         gt_s_rank1(cl, S, ldn, W.rowmap, nact, p, nact - 1, W.r, W.d1);
-                        __syncthreads();
+                        cl.sync();
                         if (warp_id() == 0) {
                             const int lane = lane_id();
                             for (int base = p; base < nact - 1; base += 32) {
@@ -1319,6 +1322,7 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
             b, n, iter0, iter1, nact, gt_reorth, gt_acc[0], gt_acc[1], gt_acc[2], gt_acc[3], gt_acc[4], gt_acc[5], gt_acc[6], gt_acc[7]);
 #endif
     // ---- results ---------------------------------------------------------------------------------------------------------------
+    if (cl.rank() != 0) return fail;
     if (B.x) for (int i = tid; i < n; i += T) B.x[(long long)b * n + i] = (fail == 2) ? 0.0 : W.x[i];
     if (B.iact) for (int i = tid; i < n; i += T) B.iact[(long long)b * n + i] = (i < nact) ? W.iact[i] : 0;
     if (tid == 0) {
@@ -1332,10 +1336,11 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
 // ---- host side (k6_thin.cu) ------------------------------------------------------------------------------------------------
 struct GtPlan {
     int threads, grid, per_sm, ok, q1s;
+    int cluster;         // CTAs per instance (0 / 1: one CTA per instance)
     size_t smem_bytes;
     long long ws_stride; // doubles of global workspace per CTA (Q1 + S)
 };
-struct GtShape { int n, meq, m, tab_doubles, ldk, ld, ss_doubles, pform; };
+struct GtShape { int n, meq, m, tab_doubles, ldk, ld, ss_doubles, pform, cluster; };
 GtPlan gt_plan(const GtShape& s, int batch, int sms, size_t smem_optin);
 size_t gt_factor_smem(int n);
 // factor `count` Hessians Q (n x n each): Jt / JtT receive count * n * n doubles, pd count flags

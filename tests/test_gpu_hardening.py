@@ -135,3 +135,24 @@ def test_download_after_thin_solve_materialises_rows(engine):
     for i in (0, 19):
         o = po.lmpc(wl.instance(bp, i), solve=False)
         assert np.array_equal(A[i], o["Aineq"]) and np.array_equal(Q[i], o["Q"])
+
+
+def test_c5_heaviest_instance_where_the_oracle_drifts(engine):
+    """C5's heaviest instance (index 1001 of the 1024: 2519 outer iterations, 1982 drops).  Same counts and the same active
+    set as the oracle; but qpgen2's in-place factor updates have drifted by then -- the ORACLE's x is 4.5e-6 away from the exact
+    solution of its own final active set, beyond the 1e-6 asked of the decision variables -- so x is held to the exact
+    active-set solution instead (1e-8), and the oracle's distance to it is recorded."""
+    from tests.util import exact_active_set_solution
+    full = wl.c5(batch=1024)
+    bp = wl.take(full, np.arange(996, 1004))
+    out = engine.lmpc_run(bp, want=("status", "iters", "control", "iact"))
+    o = po.lmpc(wl.instance(full, 1001))
+    i = 1001 - 996
+    assert out["status"][i] == 0 and o["fail"] == 0
+    assert tuple(out["iters"][i]) == tuple(o["iter"]) == (2519, 1982)
+    assert active_set(out["iact"][i]) == active_set(o["iact"])
+    xs = exact_active_set_solution(o)
+    assert x_err(out["control"][i], xs) < 1e-8
+    drift = x_err(o["x"], xs)
+    assert 1e-6 < drift < 1e-5, drift   # documents the oracle's own error; the GPU is held to the exact solution above
+    assert x_err(out["control"][i], o["control"]) < 2e-5

@@ -132,6 +132,32 @@ def test_c5(engine):
     check_batch(engine, wl.c5(batch=8))
 
 
+def test_c5_single_cta_kernel(engine, monkeypatch):
+    """the same shape with one CTA per instance (what batches of many waves use)"""
+    monkeypatch.setenv("COPRA_B200_THIN_CLUSTER", "1")
+    check_batch(engine, wl.c5(batch=4))
+
+
+def test_c5_hybrid_cluster_queue(engine, monkeypatch):
+    """longest-first queue whose head is solved by whole clusters and whose tail by single CTAs: every placement gives the
+    same iterates (identical counts and active sets, x to rounding) as the all-single-CTA run, and the oracle's on a sample"""
+    bp = wl.c5(batch=40)
+    want = ("status", "iters", "control", "iact", "nact")
+    monkeypatch.setenv("COPRA_B200_THIN_HEAVY", "5")
+    hyb = engine.lmpc_run(bp, want=want)
+    assert "thin" in engine.last_solver()
+    monkeypatch.setenv("COPRA_B200_THIN_CLUSTER", "1")
+    solo = engine.lmpc_run(bp, want=want)
+    assert np.array_equal(hyb["status"], solo["status"]) and np.array_equal(hyb["iters"], solo["iters"])
+    assert np.array_equal(hyb["iact"], solo["iact"])
+    assert np.abs(hyb["control"] - solo["control"]).max() <= 1e-9
+    heavy = np.argsort(-hyb["iters"].sum(axis=1))[:2]
+    for i in list(heavy) + [0, 39]:
+        o = po.lmpc(wl.instance(bp, int(i)))
+        assert x_err(hyb["control"][i], o["control"]) < 1e-6
+        assert active_set(hyb["iact"][i]) == active_set(o["iact"]) and tuple(hyb["iters"][i]) == tuple(o["iter"])
+
+
 def test_c5_general_kernel(engine, monkeypatch):
     monkeypatch.setenv("COPRA_B200_LEGACY_SOLVER", "1")
     check_batch(engine, wl.c5(batch=1))
