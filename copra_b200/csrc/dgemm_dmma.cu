@@ -14,10 +14,19 @@
 // The A tile of the NN case is a set of contiguous 512-byte column segments: when the operand is
 // 16-byte aligned they are fetched by the TMA engine (cp.async.bulk.shared.global + mbarrier
 // complete_tx) and overlap with the B tile's register-staged loads.
+//
+// Two kernels.  dgemm_dmma_tma_kernel (the one that runs whenever the operands are 16-byte aligned with even leading
+// dimensions) is a warp-specialised pipeline: ONE producer thread feeds a 4-stage ring of 128 x 16 (A) and 16 x 64 (B)
+// tiles with 2-D/3-D tensor-map TMA (cp.async.bulk.tensor, SWIZZLE_128B -- SASS UTMALDG), full / empty mbarriers per stage,
+// and 8 consumer warps (4 x 2, warp tile 32 x 32 = 4 x 4 DMMA tiles) read their fragments straight from the swizzled tiles;
+// out-of-range rows / columns / k are zero-filled by the TMA unit, so the main loop has no bounds code.
+// dgemm_dmma_kernel is the fallback for unaligned operands (single-buffered, register-staged loads).
 #include "launch.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace cb {
 
@@ -176,6 +185,153 @@ template <bool TRANSA> __global__ void __launch_bounds__(256) dgemm_dmma_kernel(
             }
 }
 
+
+// ---- the TMA pipeline ----------------------------------------------------------------------------------------------------
+constexpr int PM = 128, PN = 64, PK = 16, STAGES = 4;
+constexpr int A_BYTES = PM * PK * 8, B_BYTES = PN * PK * 8, STAGE_BYTES = A_BYTES + B_BYTES;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+                 : "memory");
+}
+// byte offset of element (row r, inner index i in [0,16)) of a tile whose rows are 128 bytes, SWIZZLE_128B
+__device__ __forceinline__ uint32_t swz(int r, int i) { return uint32_t(r) * 128u + (uint32_t(((i >> 1) ^ (r & 7))) << 4) + (uint32_t(i & 1) << 3); }
+
+template <bool TRANSA>
+__global__ void __launch_bounds__(288, 2) dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+    const GemmArgs g, const int zA, const int zB)
+{
+    extern __shared__ __align__(1024) unsigned char dsm_raw[];
+    __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES];
+    unsigned char* dsm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dsm_raw) + 1023) & ~uintptr_t(1023));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.x * PM, n0 = blockIdx.y * PN;
+    const int b = blockIdx.z;
+    const int M = g.M, N = g.N, K = g.K;
+    const int nk = (K + PK - 1) / PK;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 8) {
+        if (lane == 0) {
+            for (int kt = 0; kt < nk; ++kt) {
+                const int s = kt % STAGES, ph = (kt / STAGES) & 1, k0 = kt * PK;
+                if (kt >= STAGES) mbar_wait(&empty[s], uint32_t(ph ^ 1));
+                unsigned char* as = dsm + size_t(s) * STAGE_BYTES;
+                mbar_expect_tx(&full[s], STAGE_BYTES);
+                if (TRANSA) tma_load_3d(as, &tmA, k0, m0, zA ? b : 0, &full[s]);                // box {16 k, 128 m}
+                else
+                    for (int j = 0; j < PM / 16; ++j) tma_load_3d(as + j * 2048, &tmA, m0 + 16 * j, k0, zA ? b : 0, &full[s]); // box {16 m, 16 k}
+                tma_load_3d(as + A_BYTES, &tmB, k0, n0, zB ? b : 0, &full[s]);                  // box {16 k, 64 n}
+            }
+        }
+        return;
+    }
+    const int wm = warp >> 1, wn = warp & 1; // 4 x 2 consumer warps, warp tile 32 x 32
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int fr = lane >> 2, fk = lane & 3;
+    // per-lane fragment offsets inside a stage, hoisted out of the loop: everything else is an immediate
+    //   k-inner tiles (B, A of the TN case): row r = base + 8 j + fr -> swz(r, ks + fk) = r 128 + (((ks + fk) >> 1) ^ fr) 16 + (fk & 1) 8
+    //   m-inner boxes (A of the NN case):    m = wm 32 + 8 i + fr   -> (m >> 4) 2048 + (ks + fk) 128 + chunk 16 + (fr & 1) 8,
+    //                                        chunk = ((fr >> 1) ^ fk) + 4 ((i & 1) ^ ((ks >> 2) & 1))
+    uint32_t offB[4], offA[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int ks = 4 * q;
+        offB[q] = A_BYTES + swz(wn * 32 + fr, ks + fk);
+        offA[q] = TRANSA ? swz(wm * 32 + fr, ks + fk) : uint32_t(wm * 4096 + (ks + fk) * 128 + (((fr >> 1) ^ fk) << 4) + ((fr & 1) << 3));
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+        const int s = kt % STAGES, ph = (kt / STAGES) & 1;
+        mbar_wait(&full[s], uint32_t(ph));
+        const unsigned char* st = dsm + size_t(s) * STAGE_BYTES;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                af[i] = TRANSA ? *reinterpret_cast<const double*>(st + offA[q] + i * 1024)
+                               : *reinterpret_cast<const double*>(st + offA[q] + (i >> 1) * 2048 + (((i & 1) ^ (q & 1)) << 6));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = *reinterpret_cast<const double*>(st + offB[q] + j * 1024);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    double* C = g.C + (long long)b * g.sC;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int m = m0 + wm * 32 + i * 8 + fr;
+                const int n = n0 + wn * 32 + j * 8 + 2 * fk + e;
+                if (m < M && n < N) {
+                    double* cp = C + m + (long long)n * g.ldc;
+                    const double v = g.alpha * acc[i][j][e];
+                    *cp = (g.beta == 0.0) ? v : v + g.beta * (*cp);
+                }
+            }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// column-major `inner x outer` matrices, `count` of them `stride` doubles apart (0: one shared matrix)
+bool make_map(CUtensorMap* tm, const double* base, int inner, int outer, int ld, long long stride, int count, int box_inner, int box_outer)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld & 1) || (stride & 1) || ld < inner) return false;
+    const bool z = stride != 0 && count > 1;
+    cuuint64_t dims[3] = { cuuint64_t(inner), cuuint64_t(outer), cuuint64_t(z ? count : 1) };
+    cuuint64_t strides[2] = { cuuint64_t(ld) * 8, z ? cuuint64_t(stride) * 8 : cuuint64_t(ld) * 8 * cuuint64_t(outer) };
+    cuuint32_t box[3] = { cuuint32_t(box_inner), cuuint32_t(box_outer), 1 };
+    cuuint32_t estr[3] = { 1, 1, 1 };
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <bool TRANSA> cudaError_t launch_tma(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t st)
+{
+    const int smem = STAGES * STAGE_BYTES + 1024;
+    cudaError_t e = cudaFuncSetAttribute(dgemm_dmma_tma_kernel<TRANSA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); // per device
+    if (e != cudaSuccess) return e;
+    dim3 grid((g.M + PM - 1) / PM, (g.N + PN - 1) / PN, g.batch);
+    dgemm_dmma_tma_kernel<TRANSA><<<grid, 288, smem, st>>>(ta, tb, g, g.sA != 0, g.sB != 0);
+    return cudaGetLastError();
+}
+
 } // namespace
 
 int dgemm_dmma_launch(int transA, int M, int N, int K, double alpha, const double* A, int lda, long long sA, const double* B, int ldb,
@@ -190,10 +346,21 @@ int dgemm_dmma_launch(int transA, int M, int N, int K, double alpha, const doubl
         g.A = A + (long long)b0 * sA; g.lda = lda; g.sA = sA;
         g.B = B + (long long)b0 * sB; g.ldb = ldb; g.sB = sB;
         g.C = C + (long long)b0 * sC; g.ldc = ldc; g.sC = sC;
-        dim3 grid((M + TM - 1) / TM, (N + TN - 1) / TN, nb);
-        if (transA) dgemm_dmma_kernel<true><<<grid, 256, 0, st>>>(g);
-        else dgemm_dmma_kernel<false><<<grid, 256, 0, st>>>(g);
-        cudaError_t e = cudaGetLastError();
+        // tensor-map TMA pipeline when the operands qualify (16-byte aligned, even leading dimensions / batch strides)
+        static const bool no_tma = getenv("COPRA_B200_DGEMM_NO_TMA") != nullptr;
+        CUtensorMap ta, tb;
+        const bool tma = !no_tma && K >= 1 &&
+            (transA ? make_map(&ta, g.A, K, M, lda, sA, nb, PK, PM) : make_map(&ta, g.A, M, K, lda, sA, nb, 16, PK)) &&
+            make_map(&tb, g.B, K, N, ldb, sB, nb, PK, PN);
+        cudaError_t e;
+        if (tma) {
+            e = transA ? launch_tma<true>(g, ta, tb, st) : launch_tma<false>(g, ta, tb, st);
+        } else {
+            dim3 grid((M + TM - 1) / TM, (N + TN - 1) / TN, nb);
+            if (transA) dgemm_dmma_kernel<true><<<grid, 256, 0, st>>>(g);
+            else dgemm_dmma_kernel<false><<<grid, 256, 0, st>>>(g);
+            e = cudaGetLastError();
+        }
         if (e != cudaSuccess) return -int(e);
         ++launches;
     }

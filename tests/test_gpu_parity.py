@@ -291,7 +291,10 @@ def test_dgemm_dmma_primitive(engine):
     """the tensor-core FP64 GEMM behind full-size assembly: NN (TMA-fed when aligned) and TN, ragged and tiny shapes"""
     rng = np.random.default_rng(11)
     for (M, N, K, ta) in [(64, 64, 16, False), (128, 96, 64, False), (130, 70, 37, False), (5, 3, 2, False), (301, 300, 602, False),
-                          (64, 64, 16, True), (77, 33, 129, True), (300, 300, 602, True), (1, 50, 602, True)]:
+                          (64, 64, 16, True), (77, 33, 129, True), (300, 300, 602, True), (1, 50, 602, True),
+                          # even leading dimensions: the tensor-map TMA pipeline, ragged in every direction
+                          (130, 70, 38, False), (258, 130, 50, False), (2, 2, 2, False), (66, 34, 130, True), (322, 966, 320, True),
+                          (320, 966, 320, False)]:
         A = rng.normal(size=(3, K, M) if ta else (3, M, K))
         B = rng.normal(size=(3, K, N))
         C0 = rng.normal(size=(3, M, N))
