@@ -362,6 +362,30 @@ def measure_single(torch, capi, dev, local, stream, flush, config, batch, steps,
                                   ratio_to_full_step=(sum(times) / steps) / out["ms_per_step"],
                                   solved_ok=int((r.d_status == 0).sum().item()),
                                   note="copra_b200_lmpc_resolve: x0 * 0.97, condensing / Q / factor reused")
+            if "thin" in r.eng.last_solver() and r.eng.hessian_is_shared():
+                # the same re-solve with SI_warmStart(true): seeded with the previous active sets
+                r.eng.set_warm_start(True)
+                r.step_device()
+                times, its = [], None
+                for _ in range(steps):
+                    flush.fill_(3)
+                    ev0.record(stream)
+                    rc = r.lib.copra_b200_lmpc_resolve(r.eng.h, a, capi.DEVICE, C.byref(r.rd))
+                    if rc:
+                        r.eng._check(rc)
+                    ev1.record(stream)
+                    torch.cuda.synchronize()
+                    times.append(ev0.elapsed_time(ev1))
+                    if its is None:
+                        its = r.d_iters.view(-1, 2).cpu().numpy()
+                    r.step_device()  # the seed of the next timed re-solve is again the solve at the original x0
+                r.eng.set_warm_start(False)
+                out["resolve_warm"] = dict(value=bp["batch"] * steps / (sum(times) * 1e-3), unit=UNIT, ms_per_step=sum(times) / steps,
+                                           ratio_to_full_step=(sum(times) / steps) / out["ms_per_step"],
+                                           solved_ok=int((r.d_status == 0).sum().item()),
+                                           mean_iterations_after_seed=float(its[:, 0].mean()),
+                                           note="copra_b200_set_warm_start(1) + copra_b200_lmpc_resolve: x0 * 0.97, seeded with the "
+                                                "active sets of the previous solve (same optimum; opt-in, QuadProg itself has no warm start)")
         return out
     finally:
         r.close()

@@ -70,7 +70,8 @@ EXPORTS = ["copra_b200_abi_version", "copra_b200_device_count", "copra_b200_crea
            "copra_b200_lmpc_results", "copra_b200_dgemm_batch", "copra_b200_lmpc_resolve", "copra_b200_fp64_peaks",
            "copra_b200_lmpc_built_sizes", "copra_b200_last_solver", "copra_b200_hessian_is_shared", "copra_b200_multi_create", "copra_b200_multi_destroy",
            "copra_b200_multi_last_error", "copra_b200_multi_size", "copra_b200_multi_shard", "copra_b200_multi_timing",
-           "copra_b200_multi_launch_count", "copra_b200_multi_lmpc_run", "copra_b200_multi_lmpc_resolve"]
+           "copra_b200_multi_launch_count", "copra_b200_multi_lmpc_run", "copra_b200_multi_lmpc_resolve",
+           "copra_b200_set_warm_start", "copra_b200_get_warm_start", "copra_b200_multi_set_warm_start"]
 
 _lib = None
 
@@ -118,6 +119,8 @@ def load():
         lib.copra_b200_last_solver.argtypes = [C.c_void_p]
         lib.copra_b200_last_solver.restype = C.c_char_p
         lib.copra_b200_hessian_is_shared.argtypes = [C.c_void_p]
+        lib.copra_b200_set_warm_start.argtypes = [C.c_void_p, C.c_int]
+        lib.copra_b200_get_warm_start.argtypes = [C.c_void_p]
         lib.copra_b200_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
         lib.copra_b200_multi_destroy.argtypes = [C.c_void_p]
         lib.copra_b200_multi_destroy.restype = None
@@ -130,6 +133,7 @@ def load():
         lib.copra_b200_multi_launch_count.restype = C.c_longlong
         lib.copra_b200_multi_lmpc_run.argtypes = [C.c_void_p, C.POINTER(Problem), C.POINTER(Results)]
         lib.copra_b200_multi_lmpc_resolve.argtypes = [C.c_void_p, Array, C.POINTER(Results)]
+        lib.copra_b200_multi_set_warm_start.argtypes = [C.c_void_p, C.c_int]
         _lib = lib
     return _lib
 
@@ -379,6 +383,13 @@ class Engine:
         self._check(self.lib.copra_b200_fp64_peaks(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def set_warm_start(self, on=True):
+        """SI_warmStart(bool): re-solves seed the previous active sets (shared-factor thin solver only)"""
+        self._check(self.lib.copra_b200_set_warm_start(self.h, 1 if on else 0))
+
+    def warm_start(self):
+        return bool(self.lib.copra_b200_get_warm_start(self.h))
+
     def lmpc_resolve(self, x0, sizes):
         """receding-horizon re-solve of the last built batch with new initial states x0 (batch, nx)"""
         x0 = np.ascontiguousarray(np.asarray(x0, dtype=np.float64))
@@ -485,6 +496,11 @@ class MultiEngine:
             setattr(r, k, v.ctypes.data)
         self._check(self.lib.copra_b200_multi_lmpc_run(self.m, C.byref(hb.problem), C.byref(r)))
         return out
+
+    def set_warm_start(self, on=True):
+        rc = self.lib.copra_b200_multi_set_warm_start(self.m, 1 if on else 0)
+        if rc:
+            raise CopraB200Error("copra_b200_multi_set_warm_start failed (%d)" % rc)
 
     def lmpc_resolve(self, x0, sizes):
         x0 = np.ascontiguousarray(np.asarray(x0, dtype=np.float64))

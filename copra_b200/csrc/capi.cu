@@ -63,6 +63,9 @@ struct copra_b200_handle {
     bool factor_valid = false; // the thin solver's R^-1 of the last build is resident (re-solves skip the factorisation)
     bool rows_filled = false;  // Aeq / Aineq of the last build are materialised (the structured solver never reads them)
     bool use_thin = false;     // the last build is solved by the thin kernel (gi_thin.cuh)
+    bool warm_start = false;   // copra_b200_set_warm_start: re-solves seed the active set of the previous solve
+    bool warm_valid = false;   // `warm_iact` holds the active sets of the last solve of the resident build
+    bool in_resolve = false;
     bool gt_pform = false;     // ... in its shared-factor form (P = Jt Q1 kept, no factor mat-vec per pass)
     const char* solver = "";   // K5+K6 kernel(s) of the last solve
     bool nvtx_open = false;    // an NVTX stage range is open on the calling thread
@@ -590,6 +593,10 @@ int run_gt(copra_b200_handle* h, double* x, int* status, int* iters, int* nact, 
     // of constraints violated at their unconstrained minimiser (one cheap prepass) and start the heaviest first
     T.prekey = nullptr; T.preidx = nullptr; T.order = nullptr;
     T.kheavy = P.batch;
+    // warm start (opt-in): a re-solve of the resident build seeds each instance with the rows active at its previous solve
+    int* warm_iact = nullptr;
+    if (h->warm_start && pform && (rc = ws(h, "warm_iact", size_t(P.batch) * n, &warm_iact))) return rc;
+    T.warm = (h->warm_start && pform && h->in_resolve && h->warm_valid) ? warm_iact : nullptr;
     const int slots = plan.cluster > 1 ? plan.grid / plan.cluster : plan.grid; // instances in flight
     const bool lpt = P.batch > slots && (P.batch <= 24 * slots || plan.cluster > 1) && !getenv("COPRA_B200_THIN_NO_LPT");
     cudaError_t e;
@@ -614,6 +621,10 @@ int run_gt(copra_b200_handle* h, double* x, int* status, int* iters, int* nact, 
     e = gt_launch(T, plan, h->stream);
     if (e != cudaSuccess) return fail(h, COPRA_B200_E_CUDA, "gt_launch: %s", cudaGetErrorString(e));
     h->launches += 1; h->call_launches += 1;
+    if (warm_iact && iact) {
+        CU(cudaMemcpyAsync(warm_iact, iact, size_t(P.batch) * n * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+        h->warm_valid = true;
+    }
     return 0;
 }
 
@@ -822,6 +833,7 @@ int do_build(copra_b200_handle* h, const copra_b200_problem* p)
     h->sz = pl.sz;
     h->built = true;
     h->factor_valid = false;
+    h->warm_valid = false;
     h->rows_filled = !P.skip_rows;
     return 0;
 }
@@ -1125,8 +1137,21 @@ int copra_b200_lmpc_resolve(copra_b200_handle* h, copra_b200_array x0, int memor
     if ((rc = record(h, 2))) return rc;
     LAUNCHED(k4_finalize_launch(P, h->sms, h->stream));
     if ((rc = record(h, 3))) return rc;
-    return do_solve(h, r);
+    h->in_resolve = true;
+    rc = do_solve(h, r);
+    h->in_resolve = false;
+    return rc;
 }
+
+int copra_b200_set_warm_start(copra_b200_handle* h, int on)
+{
+    if (!h) return COPRA_B200_E_ARG;
+    h->warm_start = on != 0;
+    if (!on) h->warm_valid = false;
+    return 0;
+}
+
+int copra_b200_get_warm_start(const copra_b200_handle* h) { return h && h->warm_start ? 1 : 0; }
 
 int copra_b200_lmpc_results(copra_b200_handle* h, const double* x, double* control, double* trajectory, int memory)
 {

@@ -143,6 +143,13 @@ int copra_b200_multi_lmpc_run(copra_b200_multi* m, const copra_b200_problem* p, 
     });
 }
 
+int copra_b200_multi_set_warm_start(copra_b200_multi* m, int on)
+{
+    if (!m) return COPRA_B200_E_ARG;
+    for (copra_b200_handle* h : m->h) copra_b200_set_warm_start(h, on);
+    return 0;
+}
+
 int copra_b200_multi_lmpc_resolve(copra_b200_multi* m, copra_b200_array x0, const copra_b200_results* r)
 {
     if (!m) return COPRA_B200_E_ARG;

@@ -129,6 +129,7 @@ struct GtBatch {
     int* prekey;
     int* preidx;
     const int* order;
+    const int* warm; // previous active sets (n ints per instance, 1-based, 0-terminated) seeding the shared-factor form; null: cold
     int kheavy; // cluster kernel: queue entries [0, kheavy) are solved by whole clusters, the rest by single CTAs
 };
 
@@ -945,6 +946,206 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
         cl.sync();
         GT_T(0);
 
+        // ---- the two updates of the factorisation (shared by the iterations and the warm start) --------------------------------
+        auto add_column = [&](int nvl, double dd) {
+            // ---- add constraint nvl: Q1 gains zt / delta, S the column [-r/delta ; 1/delta] ----------------------
+            const double delta = sqrt(dd), inv = 1.0 / delta;
+            double* qc = q1col(nact);
+            const double* src = pform ? W.z : W.zt; // shared-factor form: the column of P = Jt Q1 is z / |zt|
+            for (int j = tid * cl.size() + cl.rank(); j < np; j += T * cl.size()) qc[j] = (j < n) ? src[j] * inv : 0.0;
+            const int newrow = W.rowmap[nact];
+            if (cl.rank() == 0) {
+                for (int i = tid; i < nact; i += T) {
+                    S[W.rowmap[i] + size_t(nact) * ldn] = -W.r[i] * inv;
+                    S[newrow + size_t(i) * ldn] = 0.0;
+                }
+                if (tid == 0) S[newrow + size_t(nact) * ldn] = inv;
+            }
+            if (tid == 0) {
+                W.iact[nact] = nvl + 1;
+                W.active[nvl] = 1;
+            }
+            ++nact;
+            cl.sync();
+        };
+        auto drop_constraint = [&](int p) {
+            cl.sync(); // (cluster: every replica has finished reading r / w before the stores below replace them)
+                        const int dropped = (tid == 0) ? W.iact[p] - 1 : 0;
+            const int prow = W.rowmap[p];
+            if (nact > 1) {
+                double vv = 0.0;
+                for (int k = tid; k < nact; k += T) { const double t_ = S[prow + size_t(k) * ldn]; W.v[k] = t_; vv += t_ * t_; }
+                vv = block_sum(vv, W.red);
+                const double rho = sqrt(vv);
+                const double vl = W.v[nact - 1];
+                const double gamma = (vl >= 0.0) ? -rho : rho;
+                const double tau = 1.0 / (rho * (rho + fabs(vl)));
+                __syncthreads();
+                if (tid == 0) W.v[nact - 1] = vl - gamma;
+                __syncthreads();
+                for (int k = tid; k < nact; k += T) W.d1[k] = tau * W.v[k];
+                // Q1 v (all rows of Q1) and S v (active rows), then the two rank-1 updates
+                if (pform) {
+                    gt_pass_rows(W, ld, q1s, nact, W.v, W.w, S, ldn, W.r, W.part);
+                    __syncthreads();
+                } else {
+                    gt_q1_row_dots(cl, W, ld, q1s, nact, W.v, W.w, W.part);
+                    __syncthreads();
+                    gt_row_dots(cl, S, ldn, nact, 0, nact, [&](int r_) { return size_t(W.rowmap[r_]); }, W.v, W.r, W.part);
+                    cl.sync();
+                }
+                gt_q1_rank1(cl, W, ld, q1s, nact - 1, W.w, W.d1);
+                gt_s_rank1(cl, S, ldn, W.rowmap, nact, p, nact - 1, W.r, W.d1);
+                cl.sync();
+                if (warp_id() == 0) {
+                    const int lane = lane_id();
+                    for (int base = p; base < nact - 1; base += 32) {
+                        const int k = base + lane;
+                        double uu = 0.0; int ia = 0, rm = 0;
+                        if (k < nact - 1) { uu = W.u[k + 1]; ia = W.iact[k + 1]; rm = W.rowmap[k + 1]; }
+                        __syncwarp();
+                        if (k < nact - 1) { W.u[k] = uu; W.iact[k] = ia; W.rowmap[k] = rm; }
+                        __syncwarp();
+                    }
+                    if (lane == 0) W.rowmap[nact - 1] = prow;
+                }
+                __syncthreads();
+            }
+            if (tid == 0) {
+                W.u[nact - 1] = W.u[nact];
+                W.u[nact] = 0.0;
+                W.iact[nact - 1] = 0;
+                W.active[dropped] = 0;
+            }
+            --nact;
+            ++iter1;
+            __syncthreads();
+        };
+
+        // ---- warm start (shared-factor form only; opt-in, SolverInterface::SI_warmStart) -------------------------------------------
+        // Seed the factorisation with the inequality / bound rows that were active at the previous solve of this instance
+        // (B.warm), solve the equality-constrained problem on that set in closed form,
+        //     s_i = slack of row i at the unconstrained minimiser,  t = -S' s,  x = x_unc + P t,  u = S t,
+        // and repair dual feasibility by dropping rows with a negative multiplier.  What is left is a valid (x, u, active set)
+        // triple of the dual method -- x minimises on the active rows, u >= 0 -- so the iterations below continue from it and
+        // stop at the same (unique) optimum; a seed row that is linearly dependent on the earlier ones is skipped.
+        if (pform && B.warm && !B.prekey) {
+            const int* wl = B.warm + (long long)b * n;
+            for (int k = tid; k < n; k += T) W.d[k] = W.x[k]; // x_unc (W.d is otherwise unused in this form)
+            __syncthreads();
+            for (int wi = 0; wi < n && nact < n; ++wi) {
+                const int id = wl[wi];
+                if (id <= 0) break;
+                const int nvl = id - 1;
+                if (nvl < meq || nvl >= q || W.active[nvl]) continue; // equalities enter through the regular iterations
+                int bj = -1;
+                double bsign = 0.0;
+                if (nvl < mg) {
+                    int fi, step, line;
+                    gt_locate(B, nvl, fi, step, line);
+                    const GtFam& F = B.fam[fi];
+                    const int supp = min(step + 1, B.N) * B.nu;
+                    for (int k = tid; k < np; k += T) {
+                        const int j = k / B.nu, bb = k - j * B.nu;
+                        W.av[k] = (k < supp) ? -gt_tab(B, W.tab, F, line, bb, step - j) : 0.0;
+                    }
+                    const double* Ef = F.E.p ? F.E.at(b) : nullptr;
+                    const double* Gf = (F.G.p && step < B.N) ? F.G.at(b) : nullptr;
+                    const double* dp = B.Hpsi + size_t(step) * B.nx * ld;
+                    const double* jp = B.Hm + size_t(step) * B.nu * ld;
+                    for (int k = tid; k < n; k += T) {
+                        double acc = 0.0;
+                        if (Ef) for (int e = 0; e < B.nx; ++e) acc = fma(Ef[line + e * F.rows], __ldg(dp + k + size_t(e) * ld), acc);
+                        if (Gf) for (int e = 0; e < B.nu; ++e) acc = fma(Gf[line + e * F.rows], __ldg(jp + k + size_t(e) * ld), acc);
+                        W.z[k] = -acc;
+                    }
+                } else {
+                    const int j = nvl - mg;
+                    if (j < n) { bj = j; bsign = -1.0; }
+                    else { bj = j - n; bsign = 1.0; }
+                    const double* hp = B.Hm + size_t(bj) * ld;
+                    for (int k = tid; k < n; k += T) W.z[k] = bsign * __ldg(hp + k);
+                }
+                __syncthreads();
+                if (nact > 0) {
+                    if (bj >= 0) { for (int c = tid; c < nact; c += T) W.d1[c] = bsign * q1col(c)[bj]; }
+                    else gt_q1_col_dots(cl, W, n, ld, q1s, nact, W.av, W.d1);
+                    __syncthreads();
+                    gt_pass_rows(W, ld, q1s, nact, W.d1, W.w, S, ldn, W.r, W.part);
+                    __syncthreads();
+                }
+                double a_za = 0.0, a_dn = 0.0;
+                for (int k = tid; k < n; k += T) {
+                    const double ak = (bj >= 0) ? (k == bj ? bsign : 0.0) : W.av[k];
+                    double zk = W.z[k];
+                    a_dn = fma(ak, zk, a_dn);
+                    if (nact > 0) { zk -= W.w[k]; W.z[k] = zk; }
+                    a_za = fma(ak, zk, a_za);
+                }
+                MinIdx none; none.v = 0.0; none.i = -1;
+                const GtPassRed pr = gt_pass_reduce(0.0, 0.0, a_za, a_dn, none, W.red + 4 * kMaxWarps, W.redi + kMaxWarps);
+                if (pr.za > 1e-10 * pr.dn) add_column(nvl, pr.za); // ends with a barrier
+                else __syncthreads();
+            }
+            if (nact > 0) {
+                // slacks of the seeded rows at x_unc (W.x still holds it)
+                if (B.ss) gt_products_ss(cl, B, W);
+                else gt_products(cl, B, W);
+                __syncthreads();
+                for (int i = tid; i < nact; i += T) {
+                    const int k = W.iact[i] - 1;
+                    double sv;
+                    if (k < mg) sv = W.bv[k] - W.sl[k];
+                    else { const int j = k - mg, v_ = j < n ? j : j - n; sv = (j < n) ? W.ub[v_] - W.x[v_] : W.x[v_] - W.lb[v_]; }
+                    W.zt[i] = sv;
+                }
+                __syncthreads();
+                for (;;) {
+                    // t = -S' s : one warp per column of S, lanes along the active rows
+                    for (int j = warp_id(); j < nact; j += (T >> 5)) {
+                        double acc = 0.0;
+                        for (int i = lane_id(); i < nact; i += 32) acc = fma(S[W.rowmap[i] + size_t(j) * ldn], W.zt[i], acc);
+                        acc = warp_sum(acc);
+                        if (lane_id() == 0) W.d1[j] = -acc;
+                    }
+                    __syncthreads();
+                    gt_pass_rows(W, ld, q1s, nact, W.d1, W.w, S, ldn, W.r, W.part); // w = P t, r = S t
+                    __syncthreads();
+                    for (int k = tid; k < n; k += T) W.x[k] = W.d[k] + W.w[k];
+                    MinIdx worst; worst.v = 0.0; worst.i = -1;
+                    for (int i = tid; i < nact; i += T) {
+                        const double ui = W.r[i];
+                        W.u[i] = ui > 0.0 ? ui : 0.0;
+                        if (ui < 0.0) { MinIdx c; c.v = ui; c.i = i; worst = better(worst, c); }
+                    }
+                    if (tid == 0) W.u[nact] = 0.0;
+                    const MinIdx wsel = block_argmin(worst, W.red, W.redi);
+                    // a multiplier that is negative only by rounding is clamped above; a really negative one leaves the seed
+                    double usc = 0.0;
+                    for (int i = tid; i < nact; i += T) usc = fmax(usc, fabs(W.r[i]));
+                    usc = block_sum(usc, W.red); // an upper bound of the scale is enough
+                    if (wsel.i < 0 || wsel.v > -1e-12 * usc) break;
+                    const int p = wsel.i;
+                    drop_constraint(p); // shifts u / iact / rowmap; the slacks follow
+                    if (warp_id() == 0) {
+                        const int lane = lane_id();
+                        for (int base = p; base < nact; base += 32) {
+                            const int k = base + lane;
+                            double sv = 0.0;
+                            if (k < nact) sv = W.zt[k + 1];
+                            __syncwarp();
+                            if (k < nact) W.zt[k] = sv;
+                            __syncwarp();
+                        }
+                    }
+                    --iter1; // a repair drop is not an iteration of the method
+                    __syncthreads();
+                    if (nact == 0) { for (int k = tid; k < n; k += T) W.x[k] = W.d[k]; __syncthreads(); break; }
+                }
+                __syncthreads();
+            }
+        }
+
         // ---- dual active-set iterations ----------------------------------------------------------------------------------------
         for (;;) {
             ++iter0;
@@ -1207,25 +1408,7 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
                     for (int i = tid; i < nact; i += T) W.u[i] -= tt * W.r[i];
                     if (tid == 0) W.u[nact] += tt;
                     if (t2min) {
-                        // ---- add constraint nvl: Q1 gains zt / delta, S the column [-r/delta ; 1/delta] ----------------------
-                        const double delta = sqrt(dd), inv = 1.0 / delta;
-                        double* qc = q1col(nact);
-                        const double* src = pform ? W.z : W.zt; // shared-factor form: the column of P = Jt Q1 is z / |zt|
-                        for (int j = tid * cl.size() + cl.rank(); j < np; j += T * cl.size()) qc[j] = (j < n) ? src[j] * inv : 0.0;
-                        const int newrow = W.rowmap[nact];
-                        if (cl.rank() == 0) {
-                            for (int i = tid; i < nact; i += T) {
-                                S[W.rowmap[i] + size_t(nact) * ldn] = -W.r[i] * inv;
-                                S[newrow + size_t(i) * ldn] = 0.0;
-                            }
-                            if (tid == 0) S[newrow + size_t(nact) * ldn] = inv;
-                        }
-                        if (tid == 0) {
-                            W.iact[nact] = nvl + 1;
-                            W.active[nvl] = 1;
-                        }
-                        ++nact;
-                        cl.sync();
+                        add_column(nvl, dd);
                         GT_T(6);
                         break; // next outer iteration
                     } else {
@@ -1256,58 +1439,7 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
                 }
                 if (do_drop) {
                     // ---- drop the it1-th active constraint: reflection with last column ~ row p of S ---------------------------
-                    cl.sync(); // (cluster: every replica has finished reading r / w before the stores below replace them)
-                    const int p = it1;
-                    const int dropped = (tid == 0) ? W.iact[p] - 1 : 0;
-                    const int prow = W.rowmap[p];
-                    if (nact > 1) {
-                        double vv = 0.0;
-                        for (int k = tid; k < nact; k += T) { const double t_ = S[prow + size_t(k) * ldn]; W.v[k] = t_; vv += t_ * t_; }
-                        vv = block_sum(vv, W.red);
-                        const double rho = sqrt(vv);
-                        const double vl = W.v[nact - 1];
-                        const double gamma = (vl >= 0.0) ? -rho : rho;
-                        const double tau = 1.0 / (rho * (rho + fabs(vl)));
-                        __syncthreads();
-                        if (tid == 0) W.v[nact - 1] = vl - gamma;
-                        __syncthreads();
-                        for (int k = tid; k < nact; k += T) W.d1[k] = tau * W.v[k];
-                        // Q1 v (all rows of Q1) and S v (active rows), then the two rank-1 updates
-                        if (pform) {
-                            gt_pass_rows(W, ld, q1s, nact, W.v, W.w, S, ldn, W.r, W.part);
-                            __syncthreads();
-                        } else {
-                            gt_q1_row_dots(cl, W, ld, q1s, nact, W.v, W.w, W.part);
-                            __syncthreads();
-                            gt_row_dots(cl, S, ldn, nact, 0, nact, [&](int r_) { return size_t(W.rowmap[r_]); }, W.v, W.r, W.part);
-                            cl.sync();
-                        }
-                        gt_q1_rank1(cl, W, ld, q1s, nact - 1, W.w, W.d1);
-                        gt_s_rank1(cl, S, ldn, W.rowmap, nact, p, nact - 1, W.r, W.d1);
-                        cl.sync();
-                        if (warp_id() == 0) {
-                            const int lane = lane_id();
-                            for (int base = p; base < nact - 1; base += 32) {
-                                const int k = base + lane;
-                                double uu = 0.0; int ia = 0, rm = 0;
-                                if (k < nact - 1) { uu = W.u[k + 1]; ia = W.iact[k + 1]; rm = W.rowmap[k + 1]; }
-                                __syncwarp();
-                                if (k < nact - 1) { W.u[k] = uu; W.iact[k] = ia; W.rowmap[k] = rm; }
-                                __syncwarp();
-                            }
-                            if (lane == 0) W.rowmap[nact - 1] = prow;
-                        }
-                        __syncthreads();
-                    }
-                    if (tid == 0) {
-                        W.u[nact - 1] = W.u[nact];
-                        W.u[nact] = 0.0;
-                        W.iact[nact - 1] = 0;
-                        W.active[dropped] = 0;
-                    }
-                    --nact;
-                    ++iter1;
-                    __syncthreads();
+                    drop_constraint(it1);
                     GT_T(7);
                     continue; // label 55
                 }

@@ -1066,8 +1066,13 @@ public:
         if (multi_) { copra_b200_multi_destroy(multi_); multi_ = nullptr; }
         const int rc = copra_b200_multi_create(devices.empty() ? nullptr : devices.data(), int(devices.size()), &multi_);
         if (rc) throw std::runtime_error("copra_b200_multi_create failed (no usable sm_100 CUDA device; there is no CPU fallback)");
+        copra_b200_multi_set_warm_start(multi_, warm_ ? 1 : 0);
     }
     int nrDevices() const { return multi_ ? copra_b200_multi_size(multi_) : 1; }
+    // SolverInterface::SI_warmStart(bool) for the batched engine (include/SolverInterface.h:42-45): resolve() seeds every
+    // instance with the active set of its previous solve.  Same optimum; fewer iterations when the active sets move little.
+    void warmStart(bool w) { warm_ = w; if (multi_) copra_b200_multi_set_warm_start(multi_, w ? 1 : 0); }
+    bool warmStart() const { return warm_; }
     copra_b200_sizes sizes()
     {
         copra_b200_sizes s{};
@@ -1096,6 +1101,7 @@ public:
             solveAndBuildTime_ = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
             return int(std::count(status_.begin(), status_.end(), 0));
         }
+        copra_b200_set_warm_start(b200::handle(), warm_ ? 1 : 0);
         b200::check(copra_b200_lmpc_run(b200::handle(), finish(), &R));
         myEpoch_ = ++b200::buildEpoch();
         copra_b200_timing tm{};
@@ -1161,6 +1167,7 @@ private:
     unsigned long myEpoch_ = ~0ul;
     copra_b200_multi* multi_ = nullptr;
     bool multiBuilt_ = false;
+    bool warm_ = false;
 };
 
 } // namespace copra

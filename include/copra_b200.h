@@ -204,6 +204,15 @@ int copra_b200_fp64_peaks(copra_b200_handle* h, double* dfma_tflops, double* dmm
  * updateSystem's condensing too).  Re-runs K4 (c = E'x0 + f, b = z - Y x0) on the resident Phi/Gs/E/f/Y/z and
  * K5..K7; Q, Aeq, Aineq are reused.  LMPC mode only (in initial-state mode x0 is a decision variable). */
 int copra_b200_lmpc_resolve(copra_b200_handle* h, copra_b200_array x0, int memory, const copra_b200_results* r);
+/* SolverInterface::SI_warmStart(bool) / SI_warmStart() (include/SolverInterface.h:42-45; QuadProg has none, the reference
+ * prints "No warmStart() function for this qp").  Opt-in: with it on, copra_b200_lmpc_resolve seeds every instance with the
+ * inequality / bound rows that were active at its previous solve on the resident build, solves that equality-constrained
+ * problem in closed form, drops the rows whose multiplier came out negative and lets the dual iterations finish from there:
+ * same optimum (the QP is strictly convex), far fewer iterations when the active set moved little.  Takes effect on builds the
+ * thin solver runs in its shared-factor form (batch-invariant system and Hessian, n > 64); ignored elsewhere.  `iters` then
+ * counts the iterations AFTER the seed. */
+int copra_b200_set_warm_start(copra_b200_handle* h, int on);
+int copra_b200_get_warm_start(const copra_b200_handle* h);
 /* K7 alone -- LMPC::updateResults (src/LMPC.cpp:282-286) for an externally solved QP: `x` holds nvar doubles per
  * instance (the SI_result() of any SolverInterface); control / trajectory as in copra_b200_results. */
 int copra_b200_lmpc_results(copra_b200_handle* h, const double* x, double* control, double* trajectory, int memory);
@@ -238,6 +247,8 @@ long long copra_b200_multi_launch_count(const copra_b200_multi* m);
 /* LMPC::solve for the whole batch (see copra_b200_lmpc_run) / receding-horizon re-solve (see copra_b200_lmpc_resolve) */
 int copra_b200_multi_lmpc_run(copra_b200_multi* m, const copra_b200_problem* p, const copra_b200_results* r);
 int copra_b200_multi_lmpc_resolve(copra_b200_multi* m, copra_b200_array x0, const copra_b200_results* r);
+/* copra_b200_set_warm_start on every shard's handle */
+int copra_b200_multi_set_warm_start(copra_b200_multi* m, int on);
 
 #ifdef __cplusplus
 }

@@ -156,3 +156,33 @@ def test_c5_heaviest_instance_where_the_oracle_drifts(engine):
     drift = x_err(o["x"], xs)
     assert 1e-6 < drift < 1e-5, drift   # documents the oracle's own error; the GPU is held to the exact solution above
     assert x_err(out["control"][i], o["control"]) < 2e-5
+
+
+@pytest.mark.parametrize("scale", [0.97, 0.4, -1.0])
+def test_warm_started_resolve_reaches_the_same_optimum(engine, scale):
+    """N1 / SI_warmStart: a re-solve seeded with the previous active sets (closed-form solve on the seed, negative multipliers
+    dropped, dual iterations from there) ends at the optimum of the cold re-solve and of the ORACLE for the new x0 -- for a
+    small move (almost nothing to do), a large one and a sign flip of x0 (most of the seed is wrong and must be repaired)"""
+    bp = wl.c3(batch=40)
+    first = engine.lmpc_run(bp)
+    x0_new = np.array(bp["x0"]) * scale
+    cold = engine.lmpc_resolve(x0_new, first["sizes"])
+    engine.set_warm_start(True)
+    try:
+        assert engine.warm_start()
+        engine.lmpc_run(bp)
+        warm = engine.lmpc_resolve(x0_new, first["sizes"])
+        again = engine.lmpc_resolve(x0_new, first["sizes"])   # seeded with its own answer: nothing left to do
+    finally:
+        engine.set_warm_start(False)
+    assert (warm["status"] == 0).all() and (cold["status"] == 0).all()
+    assert np.abs(warm["control"] - cold["control"]).max() <= 1e-8 * max(1.0, np.abs(cold["control"]).max())
+    for i in range(bp["batch"]):
+        assert active_set(warm["iact"][i], warm["nact"][i]) == active_set(cold["iact"][i], cold["nact"][i])
+    assert warm["iters"][:, 0].mean() < 0.5 * cold["iters"][:, 0].mean() or scale < 0
+    assert again["iters"][:, 0].max() == 1 and np.abs(again["control"] - warm["control"]).max() <= 1e-9
+    moved = dict(bp, x0=x0_new)
+    for i in (0, 13, 39):
+        o = po.lmpc(wl.instance(moved, i))
+        assert x_err(warm["control"][i], o["control"]) <= 1e-6
+        assert active_set(warm["iact"][i], warm["nact"][i]) == active_set(o["iact"])
