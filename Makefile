@@ -28,6 +28,6 @@ clean:
 
 # C++ facade tests (reference test scenarios against include/copra/*)
 tests/cpp/test_facade: tests/cpp/test_facade.cpp tests/cpp/systems.hpp $(wildcard include/copra/*) include/copra_b200.h $(LIB)
-	g++ -std=c++14 -O1 -Wall -Wextra -Iinclude -o $@ tests/cpp/test_facade.cpp -Lcopra_b200/lib -lcopra_b200 -Wl,-rpath,'$$ORIGIN/../../copra_b200/lib'
+	g++ -std=c++14 -O1 -Wall -Wextra -pthread -Iinclude -o $@ tests/cpp/test_facade.cpp -Lcopra_b200/lib -lcopra_b200 -Wl,-rpath,'$$ORIGIN/../../copra_b200/lib'
 
 facade-test: tests/cpp/test_facade

@@ -638,7 +638,9 @@ def main():
                 except Exception as ex:  # a secondary line must never cost the headline
                     extras[cfg] = dict(error=repr(ex))
             try:
-                extras["c3_resolve"] = measure_single(torch, capi, dev, local, stream, flush, "c3", 4096, 3, 3, resolve=True).get("resolve")
+                c3r = measure_single(torch, capi, dev, local, stream, flush, "c3", 4096, 3, 3, resolve=True)
+                extras["c3_resolve"] = c3r.get("resolve")
+                extras["c3_resolve_warm"] = c3r.get("resolve_warm")
             except Exception as ex:
                 extras["c3_resolve"] = dict(error=repr(ex))
             try:

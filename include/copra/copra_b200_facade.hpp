@@ -37,6 +37,7 @@
 #include <limits>
 #include <memory>
 #include <stdexcept>
+#include <atomic>
 #include <string>
 #include <utility>
 #include <vector>
@@ -49,7 +50,8 @@ namespace copra {
 
 namespace b200 {
 
-// One process-wide handle (device COPRA_B200_DEVICE, default 0), created on first use.
+// One engine handle PER HOST THREAD (device COPRA_B200_DEVICE, default 0), created on that thread's first use: a handle is not
+// thread-safe (include/copra_b200.h), so controllers driven from different threads never share one.
 inline copra_b200_handle* handle()
 {
     struct Holder {
@@ -65,16 +67,22 @@ inline copra_b200_handle* handle()
         }
         ~Holder() { copra_b200_destroy(h); }
     };
-    static Holder holder;
+    static thread_local Holder holder;
     return holder.h;
 }
 
-// Every call that makes the process-wide handle hold a different build bumps this counter; controllers
-// remember the epoch of their own build so that lazily fetched getters never read someone else's QP.
+// Every call that makes this thread's handle hold a different build draws a new epoch (unique across threads);
+// controllers remember the epoch of their own build so that lazily fetched getters never read someone else's QP --
+// including the QP another thread's handle holds.
 inline unsigned long& buildEpoch()
 {
-    static unsigned long epoch = 0;
+    static thread_local unsigned long epoch = 0;
     return epoch;
+}
+inline unsigned long newEpoch()
+{
+    static std::atomic<unsigned long> next{ 0 };
+    return buildEpoch() = ++next;
 }
 
 inline void check(int rc)
@@ -165,7 +173,7 @@ struct PreviewSystem {
     {
         b200::check(copra_b200_condense(b200::handle(), xDim, uDim, nrUStep, 1, b200::arr(A.data()), b200::arr(B.data()),
             b200::arr(d.data()), Phi.data(), Psi.data(), xi.data(), COPRA_B200_HOST));
-        ++b200::buildEpoch();
+        b200::newEpoch();
         isUpdated = true;
     }
 
@@ -241,7 +249,7 @@ public:
         D.p.flags = COPRA_B200_FLAG_NO_REG;
         D.costs.push_back(describe());
         b200::check(copra_b200_lmpc_build(b200::handle(), D.finish()));
-        ++b200::buildEpoch();
+        b200::newEpoch();
         b200::download(COPRA_B200_GET_Q, Q_, ps.fullUDim, ps.fullUDim);
         b200::download(COPRA_B200_GET_C, c_, ps.fullUDim);
         b200::download(COPRA_B200_GET_COST_E, E_, ps.xDim, ps.fullUDim);
@@ -447,7 +455,7 @@ public:
         D.system(ps);
         D.cstrs.push_back(describe());
         b200::check(copra_b200_lmpc_build(b200::handle(), D.finish()));
-        ++b200::buildEpoch();
+        b200::newEpoch();
         const bool eq = constraintType() == ConstraintFlag::EqualityConstraint;
         b200::download(eq ? COPRA_B200_GET_AEQ : COPRA_B200_GET_AINEQ, A_, nrConstr_, ps.fullUDim);
         b200::download(eq ? COPRA_B200_GET_BEQ : COPRA_B200_GET_BINEQ, b_, nrConstr_);
@@ -819,7 +827,7 @@ public:
             R.nact = &nact; R.iact = iact.data(); R.memory = COPRA_B200_HOST;
             native->SI_problem(sz.nvar, sz.meq, sz.mineq);
             b200::check(copra_b200_lmpc_run(h, D.finish(), &R));
-            myEpoch_ = ++b200::buildEpoch();
+            myEpoch_ = b200::newEpoch();
             native->adopt(x, status, iters, nact, iact);
             copra_b200_timing tm{};
             copra_b200_last_timing(h, &tm);
@@ -829,7 +837,7 @@ public:
         } else {
             // any other SolverInterface: K1..K4 on the GPU, the plug-in solves, K7 on the GPU
             b200::check(copra_b200_lmpc_build(h, D.finish()));
-            myEpoch_ = ++b200::buildEpoch();
+            myEpoch_ = b200::newEpoch();
             fetchMatrices(sz);
             sol_->SI_problem(sz.nvar, sz.meq, sz.mineq);
             const auto t1 = clock::now();
@@ -960,7 +968,7 @@ protected:
             describe(D);
             b200::check(copra_b200_lmpc_sizes(b200::handle(), D.finish(), &sz));
             b200::check(copra_b200_lmpc_build(b200::handle(), D.finish()));
-            myEpoch_ = ++b200::buildEpoch();
+            myEpoch_ = b200::newEpoch();
         }
         fetchMatrices(sz);
     }
@@ -1103,7 +1111,7 @@ public:
         }
         copra_b200_set_warm_start(b200::handle(), warm_ ? 1 : 0);
         b200::check(copra_b200_lmpc_run(b200::handle(), finish(), &R));
-        myEpoch_ = ++b200::buildEpoch();
+        myEpoch_ = b200::newEpoch();
         copra_b200_timing tm{};
         copra_b200_last_timing(b200::handle(), &tm);
         solveTime_ = tm.solve_ms * 1e-3;

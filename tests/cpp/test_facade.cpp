@@ -12,6 +12,7 @@
 #include <cstring>
 #include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 static int g_fail = 0, g_checks = 0;
@@ -655,6 +656,47 @@ static void batchedEntry()
     REQUIRE(ctl.iterations() == ref_it);
 }
 
+// Two host threads, each with its own controllers: every thread gets its own engine handle (b200::handle() is thread-local),
+// so the solves run concurrently and a controller solved on one thread serves its getters from a snapshot / rebuild on another.
+static void twoHostThreads()
+{
+    BoundedSystem s;
+    auto solveOne = [&s](double ud, Eigen::VectorXd* out, Eigen::MatrixXd* Qout, bool* ok) {
+        auto ps = std::make_shared<copra::PreviewSystem>();
+        ps->system(s.A, s.B, s.c, s.x0, 60);
+        copra::LMPC ctl(ps);
+        auto xCost = std::make_shared<copra::TargetCost>(s.M, s.xd);
+        Eigen::VectorXd udv(1);
+        udv << ud;
+        auto uCost = std::make_shared<copra::ControlCost>(s.N, udv);
+        auto trajConstr = std::make_shared<copra::TrajectoryBoundConstraint>(s.xLower, s.xUpper);
+        auto contConstr = std::make_shared<copra::ControlBoundConstraint>(s.uLower, s.uUpper);
+        xCost->weights(s.wx);
+        uCost->weights(s.wu);
+        ctl.addCost(xCost); ctl.addCost(uCost); ctl.addConstraint(trajConstr); ctl.addConstraint(contConstr);
+        *ok = true;
+        for (int rep = 0; rep < 5; ++rep) *ok = *ok && ctl.solve();
+        *out = ctl.control();
+        *Qout = ctl.Q();
+    };
+    Eigen::VectorXd u1, u2, r1, r2;
+    Eigen::MatrixXd Q1, Q2, Qr1, Qr2;
+    bool ok1 = false, ok2 = false, okr1 = false, okr2 = false;
+    solveOne(2.0, &r1, &Qr1, &okr1); // single-threaded references
+    solveOne(3.0, &r2, &Qr2, &okr2);
+    std::thread t1([&] { solveOne(2.0, &u1, &Q1, &ok1); });
+    std::thread t2([&] { solveOne(3.0, &u2, &Q2, &ok2); });
+    t1.join();
+    t2.join();
+    REQUIRE(ok1 && ok2 && okr1 && okr2);
+    auto same = [](const double* a, const double* b, long n) { for (long i = 0; i < n; ++i) if (a[i] != b[i]) return false; return true; };
+    REQUIRE(u1.size() == r1.size() && same(u1.data(), r1.data(), long(r1.size())));
+    REQUIRE(u2.size() == r2.size() && same(u2.data(), r2.data(), long(r2.size())));
+    REQUIRE(Q1.size() == Qr1.size() && same(Q1.data(), Qr1.data(), long(Qr1.size())));
+    REQUIRE(Q2.size() == Qr2.size() && same(Q2.data(), Qr2.data(), long(Qr2.size())));
+    REQUIRE(!same(u1.data(), u2.data(), long(u1.size())));
+}
+
 int main(int argc, char** argv)
 {
     std::setvbuf(stdout, nullptr, _IONBF, 0);
@@ -677,6 +719,7 @@ int main(int argc, char** argv)
         groups.push_back({ "LMPC_AND_INITIAL-STATE-LMPC_COMPARISON", initialStateComparison });
         groups.push_back({ "FULL_SIZE_ENTRIES_SOLVE", fullSizeEntriesSolve });
         groups.push_back({ "BATCHED_ENTRY", batchedEntry });
+        groups.push_back({ "TWO_HOST_THREADS", twoHostThreads });
     }
     for (auto& g : groups) {
         const int before = g_fail;

@@ -5,7 +5,7 @@ sys.path.insert(0, ".")
 from copra_b200 import capi, workloads as wl
 cfg, batch = sys.argv[1], int(sys.argv[2])
 ncheck = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-bp = wl.CONFIGS[cfg](batch=batch)
+bp = wl.c1() if cfg == "c1" else wl.CONFIGS[cfg](batch=batch)
 eng = capi.Engine(0)
 best = 1e9
 for _ in range(3):
