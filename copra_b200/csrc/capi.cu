@@ -477,7 +477,8 @@ bool plan_thin(copra_b200_handle* h)
     T.reorth = re ? atof(re) : 1e-2;
     // state-space evaluation of the general rows (chunks of 16 steps) when its tables fit next to everything else
     T.nx = P.nx; T.X = P.X;
-    T.ssL = 16; T.ssC = (P.N + T.ssL - 1) / T.ssL;
+    { const char* le = getenv("COPRA_B200_THIN_SS_CHUNK"); T.ssL = le ? std::max(2, atoi(le)) : 16; }
+    T.ssC = (P.N + T.ssL - 1) / T.ssL;
     int eg = 0;
     for (int k = 0; k < P.nfam; ++k) eg += P.fam[k].rows * ((P.fam[k].hasE ? P.nx : 0) + (P.fam[k].hasG ? P.nu : 0));
     T.ss_doubles = gt_ss_layout(P.nx, P.nu, P.N, T.ssL, T.ssC, eg).total;

@@ -284,8 +284,10 @@ __device__ __forceinline__ void gt_trap_mv(const CL& cl, const double* __restric
 // columns from shared memory, the rest from the global workspace
 template <class CL>
 __device__ __forceinline__ void gt_q1_col_dots(const CL& cl, const GtWork& W, int n, int ld, int q1s, int nact, const double* __restrict__ vec,
-    double* __restrict__ out)
+    double* __restrict__ out, int rows = 1 << 30)
 {
+    // `rows`: entries of vec past it are zero (the causal support of a step-size row) -- the columns are read only that far
+    const int kend = min(ld, (rows + 15) & ~15);
     const int lane = lane_id(), wp = warp_id(), nw = blockDim.x >> 5;
     const int g8 = lane >> 3, l8 = lane & 7;
     (void)n;
@@ -297,7 +299,7 @@ __device__ __forceinline__ void gt_q1_col_dots(const CL& cl, const GtWork& W, in
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
         if (on) {
             int k = 2 * l8;
-            for (; k + 48 < ld; k += 64) {
+            for (; k + 48 < kend; k += 64) {
                 const double2 a0 = *reinterpret_cast<const double2*>(col + k), a1 = *reinterpret_cast<const double2*>(col + k + 16);
                 const double2 a2 = *reinterpret_cast<const double2*>(col + k + 32), a3 = *reinterpret_cast<const double2*>(col + k + 48);
                 const double2 x0 = *reinterpret_cast<const double2*>(vec + k), x1 = *reinterpret_cast<const double2*>(vec + k + 16);
@@ -307,7 +309,7 @@ __device__ __forceinline__ void gt_q1_col_dots(const CL& cl, const GtWork& W, in
                 s2 = fma(a2.y, x2.y, fma(a2.x, x2.x, s2));
                 s3 = fma(a3.y, x3.y, fma(a3.x, x3.x, s3));
             }
-            for (; k < ld; k += 16) {
+            for (; k < kend; k += 16) {
                 const double2 a0 = *reinterpret_cast<const double2*>(col + k);
                 const double2 x0 = *reinterpret_cast<const double2*>(vec + k);
                 s0 = fma(a0.y, x0.y, fma(a0.x, x0.x, s0));
@@ -712,34 +714,80 @@ __host__ __device__ inline GtSS gt_ss_layout(int nx, int nu, int N, int L, int C
     return s;
 }
 
-// phase A of gt_products_ss for a compile-time input count (0: run-time `nu_rt`): the inner products unroll and the lag loop
-// advances two pointers
+// one entry of phase A of gt_products_ss: loc(i1 + 1)[e] = sum_{k < t} (A^k B)[e, :] u_(i1 - k); compile-time input count NU
+// (0: run-time): the inner products unroll into 128-bit shared-memory loads and the lag loop advances two pointers
 template <int NU>
-__device__ __forceinline__ void gt_ss_local(const double* __restrict__ GsL, const double* __restrict__ x, double* __restrict__ st,
-    int nx, int N, int L, int nu_rt = 0)
+__device__ __forceinline__ double gt_ss_loc(const double* __restrict__ GsL, const double* __restrict__ x, int nx, int nu, int i1, int e, int t)
+{
+    const int nxu = nx * nu;
+    const double* g = GsL + e * nu;
+    const double* u = x + i1 * nu;
+    double a0 = 0.0, a1 = 0.0;
+    int k = 0;
+    for (; k + 1 < t; k += 2, g += 2 * nxu, u -= 2 * nu) {
+        if (NU == 2 || NU == 4) {
+#pragma unroll
+            for (int bb = 0; bb < NU; bb += 2) {
+                const double2 g0 = *reinterpret_cast<const double2*>(g + bb), g1 = *reinterpret_cast<const double2*>(g + nxu + bb);
+                const double2 u0 = *reinterpret_cast<const double2*>(u + bb), u1 = *reinterpret_cast<const double2*>(u - nu + bb);
+                a0 = fma(g0.y, u0.y, fma(g0.x, u0.x, a0));
+                a1 = fma(g1.y, u1.y, fma(g1.x, u1.x, a1));
+            }
+        } else {
+            for (int bb = 0; bb < nu; ++bb) { a0 = fma(g[bb], u[bb], a0); a1 = fma(g[nxu + bb], u[bb - nu], a1); }
+        }
+    }
+    if (k < t) for (int bb = 0; bb < nu; ++bb) a0 = fma(g[bb], u[bb], a0);
+    return a0 + a1;
+}
+
+// Phases A and B of gt_products_ss.  The chunk-boundary states (phase B) are a short serial recurrence over the chunk-end
+// responses only, so two warps compute those entries first and run phase B behind a named barrier while the other warps
+// finish phase A; everybody meets at the caller's __syncthreads.
+template <int NU>
+__device__ __forceinline__ void gt_ss_local(const double* __restrict__ GsL, const double* __restrict__ PhiLL, const double* __restrict__ x,
+    double* __restrict__ st, double* __restrict__ Sc, int nx, int N, int L, int C, int nu_rt = 0)
 {
     const int nu = NU ? NU : nu_rt;
-    const int nxu = nx * nu;
-    // thread -> (step, state row): consecutive threads take consecutive rows of one step
-    int i1 = threadIdx.x / nx, e = threadIdx.x - i1 * nx;
-    const int di = blockDim.x / nx, de = blockDim.x - di * nx;
-    for (; i1 < N;) {
-        const int t = i1 % L + 1;
-        const double* g = GsL + e * nu;
-        const double* u = x + i1 * nu;
-        double a0 = 0.0, a1 = 0.0;
-        int k = 0;
-        for (; k + 1 < t; k += 2, g += 2 * nxu, u -= 2 * nu) {
-#pragma unroll
-            for (int bb = 0; bb < (NU ? NU : 1); ++bb) {
-                if (NU) { a0 = fma(g[bb], u[bb], a0); a1 = fma(g[nxu + bb], u[bb - nu], a1); }
-            }
-            if (!NU) for (int bb = 0; bb < nu; ++bb) { a0 = fma(g[bb], u[bb], a0); a1 = fma(g[nxu + bb], u[bb - nu], a1); }
+    const int tid = threadIdx.x, T = blockDim.x, nx2 = nx * nx;
+    const bool split = T >= 128 && C >= 2;
+    const int nend = split ? (C - 1) * nx : 0; // chunk-end entries (steps c L + L, c < C - 1) taken by the first two warps
+    if (split && tid < 64) {
+        for (int w = tid; w < nend; w += 64) {
+            const int c = w / nx, e = w - c * nx, i1 = (c + 1) * L - 1;
+            st[(i1 + 1) * nx + e] = gt_ss_loc<NU>(GsL, x, nx, nu, i1, e, L);
         }
-        if (k < t) for (int bb = 0; bb < nu; ++bb) a0 = fma(g[bb], u[bb], a0);
-        st[(i1 + 1) * nx + e] = a0 + a1;
-        i1 += di; e += de;
-        if (e >= nx) { e -= nx; ++i1; }
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+    } else {
+        const int t0 = split ? tid - 64 : tid, ts = split ? T - 64 : T;
+        int i1 = t0 / nx, e = t0 - i1 * nx;
+        const int di = ts / nx, de = ts - di * nx;
+        for (; i1 < N;) {
+            const int t = i1 % L + 1;
+            if (!(split && t == L && i1 + 1 <= (C - 1) * L)) st[(i1 + 1) * nx + e] = gt_ss_loc<NU>(GsL, x, nx, nu, i1, e, t);
+            i1 += di; e += de;
+            if (e >= nx) { e -= nx; ++i1; }
+        }
+    }
+    if (split ? tid < 64 : true) {
+        if (!split) __syncthreads();
+        // B: chunk-boundary states s_(c L) = sum_{c' < c} A^((c-1-c') L) loc(c' L + L)
+        for (int w = tid; w < C * nx; w += (split ? 64 : T)) {
+            const int c = w / nx, e = w - c * nx;
+            double a0 = 0.0, a1 = 0.0;
+            int cp = 0;
+            for (; cp + 1 < c; cp += 2) {
+                const double* Am = PhiLL + (c - 1 - cp) * nx2 + e;
+                const double* le = st + (cp * L + L) * nx;
+                for (int f = 0; f < nx; ++f) { a0 = fma(Am[f * nx], le[f], a0); a1 = fma(Am[f * nx - nx2], le[f + L * nx], a1); }
+            }
+            if (cp < c) {
+                const double* Am = PhiLL + (c - 1 - cp) * nx2 + e;
+                const double* le = st + (cp * L + L) * nx;
+                for (int f = 0; f < nx; ++f) a0 = fma(Am[f * nx], le[f], a0);
+            }
+            Sc[w] = a0 + a1;
+        }
     }
 }
 
@@ -756,27 +804,15 @@ __device__ __forceinline__ void gt_products_ss(const CL& cl, const GtBatch& B, c
     double* __restrict__ st = W.ss + o.oSt;
     double* __restrict__ Sc = W.ss + o.oSc;
     const double* __restrict__ EG = W.ss + o.oEG;
-    const int nxu = nx * nu, nx2 = nx * nx;
-    // A: response of each chunk to its own inputs, loc(i) = sum_{k < t} A^k B u_(i-1-k), t = i - c L
+    const int nx2 = nx * nx;
+    // A: response of each chunk to its own inputs, loc(i) = sum_{k < t} A^k B u_(i-1-k), t = i - c L;  B: boundary states
     switch (nu) {
-    case 1: gt_ss_local<1>(GsL, W.x, st, nx, N, L); break;
-    case 2: gt_ss_local<2>(GsL, W.x, st, nx, N, L); break;
-    case 4: gt_ss_local<4>(GsL, W.x, st, nx, N, L); break;
-    default: gt_ss_local<0>(GsL, W.x, st, nx, N, L, nu); break;
+    case 1: gt_ss_local<1>(GsL, PhiLL, W.x, st, Sc, nx, N, L, C); break;
+    case 2: gt_ss_local<2>(GsL, PhiLL, W.x, st, Sc, nx, N, L, C); break;
+    case 4: gt_ss_local<4>(GsL, PhiLL, W.x, st, Sc, nx, N, L, C); break;
+    default: gt_ss_local<0>(GsL, PhiLL, W.x, st, Sc, nx, N, L, C, nu); break;
     }
-    if (tid < nx) st[tid] = 0.0;
-    __syncthreads();
-    // B: chunk-boundary states s_(c L) = sum_{c' < c} A^((c-1-c') L) loc(c' L + L)
-    for (int w = tid; w < C * nx; w += T) {
-        const int c = w / nx, e = w - c * nx;
-        double a0 = 0.0;
-        for (int cp = 0; cp < c; ++cp) {
-            const double* Am = PhiLL + (c - 1 - cp) * nx2 + e;
-            const double* le = st + (cp * L + L) * nx;
-            for (int f = 0; f < nx; ++f) a0 = fma(Am[f * nx], le[f], a0);
-        }
-        Sc[w] = a0;
-    }
+    if (tid >= T - nx) st[tid - (T - nx)] = 0.0;
     __syncthreads();
     // C: s_i = loc(i) + A^t s_(c L)
     for (int w = tid + L * nx; w < N * nx; w += T) {
@@ -1038,13 +1074,13 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
                 if (id <= 0) break;
                 const int nvl = id - 1;
                 if (nvl < meq || nvl >= q || W.active[nvl]) continue; // equalities enter through the regular iterations
-                int bj = -1;
+                int bj = -1, supp = n;
                 double bsign = 0.0;
                 if (nvl < mg) {
                     int fi, step, line;
                     gt_locate(B, nvl, fi, step, line);
                     const GtFam& F = B.fam[fi];
-                    const int supp = min(step + 1, B.N) * B.nu;
+                    supp = min(step + 1, B.N) * B.nu;
                     for (int k = tid; k < np; k += T) {
                         const int j = k / B.nu, bb = k - j * B.nu;
                         W.av[k] = (k < supp) ? -gt_tab(B, W.tab, F, line, bb, step - j) : 0.0;
@@ -1069,7 +1105,7 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
                 __syncthreads();
                 if (nact > 0) {
                     if (bj >= 0) { for (int c = tid; c < nact; c += T) W.d1[c] = bsign * q1col(c)[bj]; }
-                    else gt_q1_col_dots(cl, W, n, ld, q1s, nact, W.av, W.d1);
+                    else gt_q1_col_dots(cl, W, n, ld, q1s, nact, W.av, W.d1, supp);
                     __syncthreads();
                     gt_pass_rows(W, ld, q1s, nact, W.d1, W.w, S, ldn, W.r, W.part);
                     __syncthreads();
@@ -1281,7 +1317,7 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
                         if (bj >= 0) {
                             for (int c = tid; c < nact; c += T) W.d1[c] = bsign * q1col(c)[bj];
                         } else {
-                            gt_q1_col_dots(cl, W, n, ld, q1s, nact, W.av, W.d1);
+                            gt_q1_col_dots(cl, W, n, ld, q1s, nact, W.av, W.d1, supp);
                         }
                         __syncthreads();
                         gt_pass_rows(W, ld, q1s, nact, W.d1, W.w, S, ldn, W.r, W.part);
