@@ -178,6 +178,7 @@ GtPlan gt_plan(const GtShape& sh, int batch, int sms, size_t smem_optin)
     p.smem_bytes = gt_layout(sh.n, sh.meq, sh.m, sh.tab_doubles, p.threads, q1s, sh.ss_doubles).bytes;
     p.per_sm = per_sm;
     p.grid = std::max(1, std::min(batch, sms * per_sm));
+    p.grid = std::max(1, std::min(p.grid, gt_env_int("COPRA_B200_THIN_GRID", p.grid)));
     p.ws_stride = (long long)sh.ld * sh.n + (long long)sh.n * sh.n; // Q1 (or P), S
     return p;
 }

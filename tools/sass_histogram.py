@@ -7,7 +7,7 @@ import sys
 
 txt = sys.stdin.read()
 KEYS = ["DMMA", "DFMA", "DADD", "DMUL", "LDG.E.128.CONSTANT", "LDG.E.128", "LDG.E.64.CONSTANT", "LDG.E.64", "STG.E.128", "LDS.128", "LDS.64",
-        "STS.128", "SHFL.BFLY", "REDUX", "UBLKCP.S.G", "SYNCS", "LDGSTS", "UCGABAR", "BAR.SYNC", "ATOMG", "MUFU.RSQ64H", "MUFU.RCP64H"]
+        "STS.128", "SHFL.BFLY", "REDUX", "UTMALDG", "UBLKCP.S.G", "SYNCS", "LDGSTS", "UCGABAR", "BAR.SYNC", "ATOMG", "MUFU.RSQ64H", "MUFU.RCP64H"]
 for f in re.split(r"\n\s*Function : ", txt)[1:]:
     name = f.split("\n", 1)[0].strip()
     ops = re.findall(r"^\s+/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Za-z][A-Za-z0-9_.]+)", f, re.M)
