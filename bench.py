@@ -101,16 +101,27 @@ def k6_algorithmic_flops(sz, iters):
     return (2.0 / 3.0) * n ** 3 + np.asarray(iters, dtype=np.float64) * (10.0 * n * n + 2.0 * n * q)
 
 
-def k6_executed_flops(sz, iters, drops, nact, thin, shared_hessian, batch):
-    """flops the solver kernels actually issue (estimate from the per-instance iteration / drop / active counts).
-    thin solver: per step-direction pass two triangular mat-vecs (2 n^2), the projections on Q1 (4 n a), r = S d1 (2 a^2)
-    with a = mean active count ~ nact / 2, per outer iteration the Toeplitz products (m n) and per drop two more passes
-    over Q1 and S; the factorisation (n^3: Cholesky + inverse) once per DISTINCT Hessian.
+def k6_executed_flops(sz, iters, drops, nact, thin, shared_hessian, batch, shape=None):
+    """flops the solver kernels actually issue (estimate from the per-instance iteration / drop / active counts), with
+    a = mean active count ~ nact / 2.
+    thin solver, general form (per-instance factors: C5): per step-direction pass two triangular mat-vecs (2 n^2), the
+    projections on Q1 (4 n a), r = S d1 (2 a^2); per outer iteration the Toeplitz products (m n); per drop two more passes over
+    Q1 and S; the factorisation (n^3: Cholesky + inverse) once per DISTINCT Hessian.
+    thin solver, shared-factor form (batch-invariant system and Hessian: C3): per pass d1 = P'a over the causal support (n a),
+    w = P d1 (2 n a), r = S d1 (2 a^2) and the nx + nu column reads of h (2 (nx + nu) n) -- no mat-vec with the factor; per outer
+    iteration the state-space products (2 N nx (L nu / 2 + nx) + 2 m (nx + nu)); one factorisation and three n x n x X GEMMs
+    per batch.
     dense solvers (gi_small / cluster / general): the algorithmic count with the implicit bound rows removed."""
     n, m, meq = sz["nvar"], sz["mineq"], sz["meq"]
     it, dr, na = (np.asarray(v, dtype=np.float64) for v in (iters, drops, nact))
     if thin:
         a = 0.5 * na
+        if shared_hessian and shape is not None:
+            nx, nu, N, X = shape
+            per_pass = 3.0 * n * a + 2.0 * a * a + 2.0 * (nx + nu) * n
+            prod = 2.0 * N * nx * (8.0 * nu + nx) + 2.0 * (m + meq) * (nx + nu)
+            per = (it + dr) * per_pass + it * prod + dr * (4.0 * n * a + 4.0 * a * a)
+            return float(per.sum() + float(n) ** 3 + 3.0 * 2.0 * n * n * X)
         per = (it + dr) * (2.0 * n * n + 4.0 * n * a + 2.0 * a * a) + it * (1.0 * (m + meq) * n) + dr * (4.0 * n * a + 4.0 * a * a)
         fac = float(n) ** 3 * (1.0 if shared_hessian else batch)
         return float(per.sum() + fac)
@@ -555,7 +566,8 @@ def main():
         solve_s = stage["solve_ms"] * 1e-3  # mean K5+K6 time per step of THIS rank (library CUDA events, every timed step)
         b_alg = float(k6_algorithmic_bytes(sz)) * batch
         f_alg = float(k6_algorithmic_flops(sz, iters_np[:, 0]).sum())
-        f_exec = k6_executed_flops(sz, iters_np[:, 0], iters_np[:, 1], nact_np, thin, shared_h, batch)
+        f_exec = k6_executed_flops(sz, iters_np[:, 0], iters_np[:, 1], nact_np, thin, shared_h, batch,
+                                   shape=(bp["nx"], bp["nu"], bp["N"], sz["X"]) if np.asarray(bp["A"]).ndim == 2 else None)
         t_hbm, t_fp = b_alg / (peak * 1e9), f_alg / (dfma_tf * 1e12)
         bound = "tensor" if t_fp >= t_hbm else "hbm"
         if bound == "tensor":
