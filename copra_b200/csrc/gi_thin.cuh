@@ -867,7 +867,8 @@ __device__ __forceinline__ double gt_tab(const GtBatch& B, const double* tab, co
 }
 
 // ---- the solver ----------------------------------------------------------------------------------------------------------
-template <class CL>
+// PFORM: the shared-factor form (GtBatch::Hpsi != null), a compile-time switch so that each kernel carries one form only
+template <bool PFORM, class CL>
 __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, int b, double vsmall, int max_iter)
 {
     const int n = B.n, meq = B.meq, m = B.m, mg = meq + m, q = mg + 2 * n, np = gt_even(n);
@@ -882,7 +883,7 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
     const double* gAeq = B.Aeq.p ? B.Aeq.at(b) : nullptr;
     const double* gAin = B.Aineq.p ? B.Aineq.at(b) : nullptr;
     auto q1col = [&](int c) -> double* { return (c < q1s ? W.Q1s : W.Q1) + size_t(c) * ld; };
-    const bool pform = B.Hpsi != nullptr; // shared-factor form: z = H a - P d1 (see GtBatch::Hpsi)
+    constexpr bool pform = PFORM; // shared-factor form: z = H a - P d1 (see GtBatch::Hpsi)
 
     // ---- 0. load ----------------------------------------------------------------------------------------------------------
     if (B.structured) {

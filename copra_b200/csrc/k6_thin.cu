@@ -74,7 +74,7 @@ cudaError_t gt_psit_fill_launch(const double* Gs, double* PsiT, int nx, int nu, 
     return cudaGetLastError();
 }
 
-template <int MAXT, int MINB>
+template <int MAXT, int MINB, bool PFORM>
 __global__ void __launch_bounds__(MAXT, MINB) gi_thin_kernel(const __grid_constant__ GtBatch B)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(MAXT, MINB) gi_thin_kernel(const __grid_consta
         __syncthreads();
         if (q >= B.batch) break;
         const int b = B.order ? B.order[q] : q; // longest-first when a prepass ranked the instances
-        gt_solve(GtSolo(), B, W, b, B.vsmall, B.max_iter);
+        gt_solve<PFORM>(GtSolo(), B, W, b, B.vsmall, B.max_iter);
         __syncthreads();
     }
 }
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(MAXT, 1) gi_thin_cluster_kernel(const __grid_c
         if (q >= B.batch) return;
         if (q >= B.kheavy) break;
         const int b = B.order ? B.order[q] : q;
-        gt_solve(cl, B, W, b, B.vsmall, B.max_iter);
+        gt_solve<false>(cl, B, W, b, B.vsmall, B.max_iter);
         cl.sync(); // every CTA is done with this instance (and has read s_next) before the next index or a remote store arrives
     }
     // throughput phase: the rest of the queue, one CTA per instance (2.2x more work per SM-second than a cluster); the index
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(MAXT, 1) gi_thin_cluster_kernel(const __grid_c
         }
         if (q >= B.batch) break;
         const int b = B.order ? B.order[q] : q;
-        gt_solve(GtSolo(), B, W, b, B.vsmall, B.max_iter);
+        gt_solve<false>(GtSolo(), B, W, b, B.vsmall, B.max_iter);
         q = -1;
     }
 }
@@ -150,7 +150,9 @@ GtPlan gt_plan(const GtShape& sh, int batch, int sms, size_t smem_optin)
 {
     GtPlan p{};
     p.threads = gt_env_int("COPRA_B200_THIN_THREADS", 512);
-    if (p.threads != 256 && p.threads != 512 && p.threads != 1024) p.threads = 512;
+    // 512 threads per instance: 256 (47.7 k solves/s on C3) and 1024 x 1 CTA/SM (51.1 k) were measured against 512 x 2 (63.0 k) and
+    // dropped -- every extra instantiation of the solver costs minutes of compile time
+    p.threads = 512;
     const size_t base = gt_layout(sh.n, sh.meq, sh.m, sh.tab_doubles, p.threads, 0, sh.ss_doubles).bytes;
     p.ok = base + 2048 <= smem_optin;
     if (!p.ok) return p;
@@ -194,11 +196,11 @@ cudaError_t gt_factor_launch(DArr Q, int n, int ld, int count, double* Jt, doubl
     return cudaGetLastError();
 }
 
-template <int MAXT, int MINB> static cudaError_t gt_launch_t(const GtBatch& B, const GtPlan& plan, cudaStream_t st)
+template <int MAXT, int MINB, bool PFORM> static cudaError_t gt_launch_t(const GtBatch& B, const GtPlan& plan, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(gi_thin_kernel<MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes));
+    cudaError_t e = cudaFuncSetAttribute(gi_thin_kernel<MAXT, MINB, PFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes));
     if (e != cudaSuccess) return e;
-    gi_thin_kernel<MAXT, MINB><<<plan.grid, plan.threads, plan.smem_bytes, st>>>(B);
+    gi_thin_kernel<MAXT, MINB, PFORM><<<plan.grid, plan.threads, plan.smem_bytes, st>>>(B);
     return cudaGetLastError();
 }
 
@@ -230,7 +232,7 @@ template <int MAXT> static int gt_cluster_capacity_t(const GtPlan& plan, int csi
 // resident clusters of `csize` CTAs for this plan (0: cannot be scheduled)
 int gt_cluster_capacity(const GtPlan& plan, int csize)
 {
-    return plan.threads <= 512 ? gt_cluster_capacity_t<512>(plan, csize) : gt_cluster_capacity_t<1024>(plan, csize);
+    return gt_cluster_capacity_t<512>(plan, csize);
 }
 
 template <int MAXT> static cudaError_t gt_launch_cluster_t(const GtBatch& B, const GtPlan& plan, cudaStream_t st)
@@ -256,10 +258,10 @@ cudaError_t gt_sort_launch(const int* keys, int* keys_sorted, const int* idx, in
 
 cudaError_t gt_launch(const GtBatch& B, const GtPlan& plan, cudaStream_t st)
 {
-    if (plan.cluster > 1) return plan.threads <= 512 ? gt_launch_cluster_t<512>(B, plan, st) : gt_launch_cluster_t<1024>(B, plan, st);
-    if (plan.threads <= 256) return gt_launch_t<256, 2>(B, plan, st);
-    if (plan.threads <= 512) return plan.per_sm >= 2 ? gt_launch_t<512, 2>(B, plan, st) : gt_launch_t<512, 1>(B, plan, st);
-    return gt_launch_t<1024, 1>(B, plan, st);
+    if (plan.cluster > 1) return gt_launch_cluster_t<512>(B, plan, st);
+    // shared-factor form (C3-like batches: 2 CTAs/SM whenever it applies) / general form
+    if (B.Hpsi) return plan.per_sm >= 2 ? gt_launch_t<512, 2, true>(B, plan, st) : gt_launch_t<512, 1, true>(B, plan, st);
+    return plan.per_sm >= 2 ? gt_launch_t<512, 2, false>(B, plan, st) : gt_launch_t<512, 1, false>(B, plan, st);
 }
 
 } // namespace cb
