@@ -867,8 +867,10 @@ __device__ __forceinline__ double gt_tab(const GtBatch& B, const double* tab, co
 }
 
 // ---- the solver ----------------------------------------------------------------------------------------------------------
-// PFORM: the shared-factor form (GtBatch::Hpsi != null), a compile-time switch so that each kernel carries one form only
-template <bool PFORM, class CL>
+// FORM is a compile-time switch so that each kernel carries the code of one form only (less code, fewer spills: +10% on C3):
+//   0 general form (per-instance factors)   1 shared-factor form (GtBatch::Hpsi != null), any row path, warm start
+//   2 shared-factor form + state-space products, cold start: the C3 hot path
+template <int FORM, class CL>
 __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, int b, double vsmall, int max_iter)
 {
     const int n = B.n, meq = B.meq, m = B.m, mg = meq + m, q = mg + 2 * n, np = gt_even(n);
@@ -883,10 +885,12 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
     const double* gAeq = B.Aeq.p ? B.Aeq.at(b) : nullptr;
     const double* gAin = B.Aineq.p ? B.Aineq.at(b) : nullptr;
     auto q1col = [&](int c) -> double* { return (c < q1s ? W.Q1s : W.Q1) + size_t(c) * ld; };
-    constexpr bool pform = PFORM; // shared-factor form: z = H a - P d1 (see GtBatch::Hpsi)
+    constexpr bool pform = FORM >= 1; // shared-factor form: z = H a - P d1 (see GtBatch::Hpsi)
+    const bool use_ss = (FORM == 2) ? true : (B.ss != 0);                // compile-time in the hot kernel: the other row paths vanish
+    const bool structured = (FORM == 2) ? true : (B.structured != 0);
 
     // ---- 0. load ----------------------------------------------------------------------------------------------------------
-    if (B.structured) {
+    if (structured) {
         for (int fi = 0; fi < B.nfam; ++fi) {
             const GtFam& F = B.fam[fi];
             const double* src = F.EGx + (long long)b * F.sEGx;
@@ -897,7 +901,7 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
             }
         }
     }
-    if (B.ss) {
+    if (use_ss) {
         const int nx = B.nx, nu = B.nu, L = B.ssL, C = B.ssC, Xr = B.X, Nnx = B.N * nx;
         const GtSS& o = B.ssl;
         const double* gPhi = B.Phi.at(b);
@@ -961,7 +965,7 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
         // ---- norms of the general rows (the reference's summation order: columns ascending) ---------------------------------
         for (int i = tid; i < mg; i += T) {
             double s = 0.0;
-            if (B.structured) {
+            if (structured) {
                 int fi, step, line;
                 gt_locate(B, i, fi, step, line);
                 const GtFam& F = B.fam[fi];
@@ -1066,7 +1070,7 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
         // and repair dual feasibility by dropping rows with a negative multiplier.  What is left is a valid (x, u, active set)
         // triple of the dual method -- x minimises on the active rows, u >= 0 -- so the iterations below continue from it and
         // stop at the same (unique) optimum; a seed row that is linearly dependent on the earlier ones is skipped.
-        if (pform && B.warm && !B.prekey) {
+        if (FORM == 1 && B.warm && !B.prekey) {
             const int* wl = B.warm + (long long)b * n;
             for (int k = tid; k < n; k += T) W.d[k] = W.x[k]; // x_unc (W.d is otherwise unused in this form)
             __syncthreads();
@@ -1126,7 +1130,7 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
             }
             if (nact > 0) {
                 // slacks of the seeded rows at x_unc (W.x still holds it)
-                if (B.ss) gt_products_ss(cl, B, W);
+                if (use_ss) gt_products_ss(cl, B, W);
                 else gt_products(cl, B, W);
                 __syncthreads();
                 for (int i = tid; i < nact; i += T) {
@@ -1189,8 +1193,8 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
             if (iter0 > max_iter) { fail = 3; break; }
             // all slacks; most violated normalised constraint, lowest index on ties
             if (mg > 0) {
-                if (B.ss) gt_products_ss(cl, B, W);
-                else if (B.structured) gt_products(cl, B, W);
+                if (use_ss) gt_products_ss(cl, B, W);
+                else if (structured) gt_products(cl, B, W);
                 else {
                     if (meq) gt_row_dots(cl, gAeq, size_t(meq), meq, 0, n, [](int r_) { return size_t(r_); }, W.x, W.sl, W.part);
                     if (meq && m) __syncthreads();
@@ -1241,7 +1245,7 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
             int hfi = 0, hstep = 0, hline = 0;
             if (nvl < mg) {
                 const double sg = (nvl < meq) ? double(W.sgn[nvl]) : -1.0;
-                if (B.structured) {
+                if (structured) {
                     gt_locate(B, nvl, hfi, hstep, hline);
                     const GtFam& F = B.fam[hfi];
                     supp = min(hstep + 1, B.N) * B.nu;
@@ -1256,7 +1260,7 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
                 }
                 if (pform) {
                     // d is never formed
-                } else if (B.structured && B.Dpsi) {
+                } else if (structured && B.Dpsi) {
                     const GtFam& F = B.fam[hfi];
                     const double* Ef = F.E.p ? F.E.at(b) : nullptr;
                     const double* Gf = (F.G.p && hstep < B.N) ? F.G.at(b) : nullptr;

@@ -74,7 +74,7 @@ cudaError_t gt_psit_fill_launch(const double* Gs, double* PsiT, int nx, int nu, 
     return cudaGetLastError();
 }
 
-template <int MAXT, int MINB, bool PFORM>
+template <int MAXT, int MINB, int FORM>
 __global__ void __launch_bounds__(MAXT, MINB) gi_thin_kernel(const __grid_constant__ GtBatch B)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(MAXT, MINB) gi_thin_kernel(const __grid_consta
         __syncthreads();
         if (q >= B.batch) break;
         const int b = B.order ? B.order[q] : q; // longest-first when a prepass ranked the instances
-        gt_solve<PFORM>(GtSolo(), B, W, b, B.vsmall, B.max_iter);
+        gt_solve<FORM>(GtSolo(), B, W, b, B.vsmall, B.max_iter);
         __syncthreads();
     }
 }
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(MAXT, 1) gi_thin_cluster_kernel(const __grid_c
         if (q >= B.batch) return;
         if (q >= B.kheavy) break;
         const int b = B.order ? B.order[q] : q;
-        gt_solve<false>(cl, B, W, b, B.vsmall, B.max_iter);
+        gt_solve<0>(cl, B, W, b, B.vsmall, B.max_iter);
         cl.sync(); // every CTA is done with this instance (and has read s_next) before the next index or a remote store arrives
     }
     // throughput phase: the rest of the queue, one CTA per instance (2.2x more work per SM-second than a cluster); the index
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(MAXT, 1) gi_thin_cluster_kernel(const __grid_c
         }
         if (q >= B.batch) break;
         const int b = B.order ? B.order[q] : q;
-        gt_solve<false>(GtSolo(), B, W, b, B.vsmall, B.max_iter);
+        gt_solve<0>(GtSolo(), B, W, b, B.vsmall, B.max_iter);
         q = -1;
     }
 }
@@ -196,11 +196,11 @@ cudaError_t gt_factor_launch(DArr Q, int n, int ld, int count, double* Jt, doubl
     return cudaGetLastError();
 }
 
-template <int MAXT, int MINB, bool PFORM> static cudaError_t gt_launch_t(const GtBatch& B, const GtPlan& plan, cudaStream_t st)
+template <int MAXT, int MINB, int FORM> static cudaError_t gt_launch_t(const GtBatch& B, const GtPlan& plan, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(gi_thin_kernel<MAXT, MINB, PFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes));
+    cudaError_t e = cudaFuncSetAttribute(gi_thin_kernel<MAXT, MINB, FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes));
     if (e != cudaSuccess) return e;
-    gi_thin_kernel<MAXT, MINB, PFORM><<<plan.grid, plan.threads, plan.smem_bytes, st>>>(B);
+    gi_thin_kernel<MAXT, MINB, FORM><<<plan.grid, plan.threads, plan.smem_bytes, st>>>(B);
     return cudaGetLastError();
 }
 
@@ -260,8 +260,10 @@ cudaError_t gt_launch(const GtBatch& B, const GtPlan& plan, cudaStream_t st)
 {
     if (plan.cluster > 1) return gt_launch_cluster_t<512>(B, plan, st);
     // shared-factor form (C3-like batches: 2 CTAs/SM whenever it applies) / general form
-    if (B.Hpsi) return plan.per_sm >= 2 ? gt_launch_t<512, 2, true>(B, plan, st) : gt_launch_t<512, 1, true>(B, plan, st);
-    return plan.per_sm >= 2 ? gt_launch_t<512, 2, false>(B, plan, st) : gt_launch_t<512, 1, false>(B, plan, st);
+    if (B.Hpsi && B.ss && B.structured && !B.warm && !B.prekey)
+        return plan.per_sm >= 2 ? gt_launch_t<512, 2, 2>(B, plan, st) : gt_launch_t<512, 1, 2>(B, plan, st);
+    if (B.Hpsi) return plan.per_sm >= 2 ? gt_launch_t<512, 2, 1>(B, plan, st) : gt_launch_t<512, 1, 1>(B, plan, st);
+    return plan.per_sm >= 2 ? gt_launch_t<512, 2, 0>(B, plan, st) : gt_launch_t<512, 1, 0>(B, plan, st);
 }
 
 } // namespace cb
