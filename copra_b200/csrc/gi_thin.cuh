@@ -26,6 +26,7 @@
 #include "engine.cuh"
 #include "gi_solver.cuh"
 #include <cooperative_groups.h>
+#include <cfloat>
 #ifdef GT_PROFILE
 #include <cstdio>
 #define GT_T(k) do { const long long t1_ = clock64(); gt_acc[k] += t1_ - gt_t0; gt_t0 = t1_; } while (0)
@@ -169,7 +170,7 @@ __host__ __device__ inline GtLayout gt_layout(int n, int meq, int m, int tab_dou
     size_t b = o * sizeof(double);
     L.oIact = b; b += sizeof(int) * size_t(n);
     L.oRowmap = b; b += sizeof(int) * size_t(n);
-    L.oRedI = b; b += sizeof(int) * 2 * kMaxWarps;
+    L.oRedI = b; b += sizeof(int) * 3 * kMaxWarps;
     L.oActive = b; b += size_t(mg + 2 * n);
     L.oSgn = b; b += size_t(meq > 0 ? meq : 1);
     L.bytes = (b + 15) & ~size_t(15);
@@ -791,9 +792,10 @@ __device__ __forceinline__ void gt_ss_local(const double* __restrict__ GsL, cons
     }
 }
 
-// sl[row] for every general row through the state-space form (see GtBatch::ss); fixed summation order (deterministic)
-template <class CL>
-__device__ __forceinline__ void gt_products_ss(const CL& cl, const GtBatch& B, const GtWork& W)
+// value of every general row through the state-space form (see GtBatch::ss), handed to emit(row in [eq | ineq], value) by
+// the thread that formed it; fixed summation order (deterministic)
+template <class CL, class EMIT>
+__device__ __forceinline__ void gt_products_ss(const CL& cl, const GtBatch& B, const GtWork& W, EMIT emit)
 {
     const int nx = B.nx, nu = B.nu, N = B.N, L = B.ssL, C = B.ssC;
     const int tid = threadIdx.x, T = blockDim.x;
@@ -834,13 +836,13 @@ __device__ __forceinline__ void gt_products_ss(const CL& cl, const GtBatch& B, c
         if (F.E.p) eg += r * nx;
         const double* Gf = F.G.p ? EG + eg : nullptr;
         if (F.G.p) eg += r * nu;
-        double* out = W.sl + (F.is_eq ? 0 : B.meq) + F.row_off;
+        const int row0 = (F.is_eq ? 0 : B.meq) + F.row_off;
         for (int w = tid; w < cnt; w += T) {
             const int si = w / r, line = w - si * r, step = F.i0 + si;
             double a0 = 0.0;
             if (Ef) for (int e = 0; e < nx; ++e) a0 = fma(Ef[line + e * r], st[step * nx + e], a0);
             if (Gf && step < N) for (int bb = 0; bb < nu; ++bb) a0 = fma(Gf[line + bb * r], W.x[step * nu + bb], a0);
-            cl.put(out + w, a0);
+            emit(row0 + w, a0);
         }
     }
 }
@@ -948,6 +950,14 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
 
     int fail = 0, nact = 0, iter0 = 0, iter1 = 0;
     if (B.pd[(long long)b * B.pd_stride] == 0) fail = 2;
+    // no finite bound on any variable (the 2n rows QuadProgDenseSolver appends are +-DBL_MAX / +-inf): they can never be
+    // violated, so the selection skips them
+    bool nobounds;
+    {
+        int fin = 0;
+        for (int i = tid; i < n; i += T) fin |= (W.lb[i] > -DBL_MAX) || (W.ub[i] < DBL_MAX);
+        nobounds = __syncthreads_or(fin) == 0;
+    }
     if (B.prekey && fail != 0) {
         if (tid == 0 && cl.rank() == 0) { B.prekey[b] = 0; B.preidx[b] = b; }
         return fail;
@@ -1130,7 +1140,7 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
             }
             if (nact > 0) {
                 // slacks of the seeded rows at x_unc (W.x still holds it)
-                if (use_ss) gt_products_ss(cl, B, W);
+                if (use_ss) gt_products_ss(cl, B, W, [&](int row, double v) { cl.put(W.sl + row, v); });
                 else gt_products(cl, B, W);
                 __syncthreads();
                 for (int i = tid; i < nact; i += T) {
@@ -1192,24 +1202,12 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
             ++iter0;
             if (iter0 > max_iter) { fail = 3; break; }
             // all slacks; most violated normalised constraint, lowest index on ties
-            if (mg > 0) {
-                if (use_ss) gt_products_ss(cl, B, W);
-                else if (structured) gt_products(cl, B, W);
-                else {
-                    if (meq) gt_row_dots(cl, gAeq, size_t(meq), meq, 0, n, [](int r_) { return size_t(r_); }, W.x, W.sl, W.part);
-                    if (meq && m) __syncthreads();
-                    if (m) gt_row_dots(cl, gAin, size_t(m), m, 0, n, [](int r_) { return size_t(r_); }, W.x, W.sl + meq, W.part);
-                }
-            }
-            cl.sync();
-            GT_T(1);
             MinIdx best; best.v = 0.0; best.i = -1;
-            double best_s = 0.0;
             int nviol = 0;
-            for (int i = tid; i < q; i += T) {
+            auto consider = [&](int i, double slv) {
                 double s;
-                if (i < meq) s = double(W.sgn[i]) * (W.sl[i] - W.bv[i]);
-                else if (i < mg) s = W.bv[i] - W.sl[i];
+                if (i < meq) s = double(W.sgn[i]) * (slv - W.bv[i]);
+                else if (i < mg) s = W.bv[i] - slv;
                 else s = gi_bound_slack(i - mg, n, mg, W.x, W.lb, W.ub, W.active);
                 if (fabs(s) < vsmall) s = 0.0;
                 if (i < meq) {
@@ -1221,12 +1219,41 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
                 if (s < 0.0) {
                     const double nrm = (i < mg) ? W.norm[i] : 1.0;
                     MinIdx c; c.v = s / nrm; c.i = i;
-                    const MinIdx nb = better(best, c);
-                    if (nb.i != best.i) best_s = s;
-                    best = nb;
+                    best = better(best, c);
+                }
+            };
+            // hot kernel: the thread that forms a row judges it at once -- no barrier between the products and the selection
+            constexpr bool fused = FORM == 2 && !CL::multi;
+            if (mg > 0) {
+                if (fused) gt_products_ss(cl, B, W, [&](int row, double v) { W.sl[row] = v; consider(row, v); });
+                else if (use_ss) gt_products_ss(cl, B, W, [&](int row, double v) { cl.put(W.sl + row, v); });
+                else if (structured) gt_products(cl, B, W);
+                else {
+                    if (meq) gt_row_dots(cl, gAeq, size_t(meq), meq, 0, n, [](int r_) { return size_t(r_); }, W.x, W.sl, W.part);
+                    if (meq && m) __syncthreads();
+                    if (m) gt_row_dots(cl, gAin, size_t(m), m, 0, n, [](int r_) { return size_t(r_); }, W.x, W.sl + meq, W.part);
                 }
             }
-            const MinIdx sel = block_argmin(best, W.red, W.redi);
+            if (!fused) {
+                cl.sync();
+                for (int i = tid; i < mg; i += T) consider(i, W.sl[i]);
+            }
+            GT_T(1);
+            if (!nobounds) for (int i = mg + tid; i < q; i += T) consider(i, 0.0);
+            // ONE barrier: per-warp winners to a scratch of their own, every warp finishes the arg-min redundantly
+            MinIdx sel;
+            {
+                const MinIdx wbest = warp_argmin(best);
+                double* sv = W.red + 9 * kMaxWarps;
+                int* si = W.redi + 2 * kMaxWarps;
+                if (lane_id() == 0) { sv[warp_id()] = wbest.v; si[warp_id()] = wbest.i; }
+                __syncthreads();
+                MinIdx t_;
+                const bool on = lane_id() < (T >> 5);
+                t_.v = on ? sv[lane_id()] : 0.0;
+                t_.i = on ? si[lane_id()] : -1;
+                sel = warp_argmin(t_);
+            }
             if (B.prekey) { // prepass: only the difficulty estimate is wanted
                 const double cnt = block_sum(double(nviol), W.red);
                 if (tid == 0 && cl.rank() == 0) { B.prekey[b] = int(cnt); B.preidx[b] = b; }
@@ -1234,9 +1261,11 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
             }
             if (sel.i < 0) break; // optimal
             const int nvl = sel.i;
-            if (best.i == nvl) scal[0] = best_s;
-            __syncthreads();
-            double s_nvl = scal[0];
+            // its slack, recomputed by every thread from the published values (equalities: the sign was already turned)
+            double s_nvl;
+            if (nvl < meq) s_nvl = -fabs(W.sl[nvl] - W.bv[nvl]);
+            else if (nvl < mg) s_nvl = W.bv[nvl] - W.sl[nvl];
+            else s_nvl = gi_bound_slack(nvl - mg, n, mg, W.x, W.lb, W.ub, W.active);
             GT_T(2);
 
             // the signed normal a_nvl (quadprog orientation a'x >= b) and d = Jt' a: they do not change at label 55
@@ -1303,7 +1332,6 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
                     }
                 }
             };
-            if (pform) load_h();
             cl.sync();
             double dnorm2 = 0.0;
             if (!pform) {
@@ -1317,7 +1345,7 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
                 MinIdx t1m;
                 if (pform) {
                     // ---- shared-factor form: d1 = P' a ; [w, r] = [P, S] d1 ; z = h - w ; |zt|^2 = a'z ; |d|^2 = a'h -----------------
-                    if (pass > 0) { load_h(); __syncthreads(); }
+                    load_h(); // every thread reads back only the entries it wrote: the loads overlap with the sweeps below
                     if (nact > 0) {
                         if (bj >= 0) {
                             for (int c = tid; c < nact; c += T) W.d1[c] = bsign * q1col(c)[bj];
