@@ -310,10 +310,18 @@ __device__ __forceinline__ void gt_q1_col_dots(const CL& cl, const GtWork& W, in
                 s2 = fma(a2.y, x2.y, fma(a2.x, x2.x, s2));
                 s3 = fma(a3.y, x3.y, fma(a3.x, x3.x, s3));
             }
-            for (; k < kend; k += 16) {
+            if (k < kend) { // up to three 16-row slices left: one round trip
+                const bool h1 = k + 16 < kend, h2 = k + 32 < kend;
+                const double2 zero = make_double2(0.0, 0.0);
                 const double2 a0 = *reinterpret_cast<const double2*>(col + k);
+                const double2 a1 = h1 ? *reinterpret_cast<const double2*>(col + k + 16) : zero;
+                const double2 a2 = h2 ? *reinterpret_cast<const double2*>(col + k + 32) : zero;
                 const double2 x0 = *reinterpret_cast<const double2*>(vec + k);
+                const double2 x1 = h1 ? *reinterpret_cast<const double2*>(vec + k + 16) : zero;
+                const double2 x2 = h2 ? *reinterpret_cast<const double2*>(vec + k + 32) : zero;
                 s0 = fma(a0.y, x0.y, fma(a0.x, x0.x, s0));
+                s1 = fma(a1.y, x1.y, fma(a1.x, x1.x, s1));
+                s2 = fma(a2.y, x2.y, fma(a2.x, x2.x, s2));
             }
         }
         double q = (s0 + s1) + (s2 + s3);
@@ -541,10 +549,16 @@ __device__ __forceinline__ void gt_pass_rows(const GtWork& W, int ld, int q1s, i
                 q2.x = fma(a2.x, v2, q2.x); q2.y = fma(a2.y, v2, q2.y);
                 q3.x = fma(a3.x, v3, q3.x); q3.y = fma(a3.y, v3, q3.y);
             }
-            for (; c < nact; c += G, cp += cs, vp += G) {
+            if (c < nact) { // up to three columns left: their loads go out together (one round trip, not three)
+                const bool h1 = c + G < nact, h2 = c + 2 * G < nact;
+                const double2 zero = make_double2(0.0, 0.0);
                 const double2 a0 = *reinterpret_cast<const double2*>(cp);
-                const double v0 = vp[0];
+                const double2 a1 = h1 ? *reinterpret_cast<const double2*>(cp + cs) : zero;
+                const double2 a2 = h2 ? *reinterpret_cast<const double2*>(cp + 2 * cs) : zero;
+                const double v0 = vp[0], v1 = h1 ? vp[G] : 0.0, v2 = h2 ? vp[2 * G] : 0.0;
                 q0.x = fma(a0.x, v0, q0.x); q0.y = fma(a0.y, v0, q0.y);
+                q1.x = fma(a1.x, v1, q1.x); q1.y = fma(a1.y, v1, q1.y);
+                q2.x = fma(a2.x, v2, q2.x); q2.y = fma(a2.y, v2, q2.y);
             }
             *reinterpret_cast<double2*>(partQ + 2 * (g * rp + pr)) = make_double2((q0.x + q1.x) + (q2.x + q3.x), (q0.y + q1.y) + (q2.y + q3.y));
         }
@@ -562,7 +576,11 @@ __device__ __forceinline__ void gt_pass_rows(const GtWork& W, int ld, int q1s, i
                 const double m0 = sr[0], m1 = sr[cs], m2 = sr[2 * cs], m3 = sr[3 * cs];
                 s0 = fma(m0, vp[0], s0); s1 = fma(m1, vp[GS], s1); s2 = fma(m2, vp[2 * GS], s2); s3 = fma(m3, vp[3 * GS], s3);
             }
-            for (; c < nact; c += GS, sr += cs, vp += GS) s0 = fma(sr[0], vp[0], s0);
+            if (c < nact) {
+                const bool h1 = c + GS < nact, h2 = c + 2 * GS < nact;
+                const double m0 = sr[0], m1 = h1 ? sr[cs] : 0.0, m2 = h2 ? sr[2 * cs] : 0.0;
+                s0 = fma(m0, vp[0], s0); s1 = fma(m1, h1 ? vp[GS] : 0.0, s1); s2 = fma(m2, h2 ? vp[2 * GS] : 0.0, s2);
+            }
             partS[g * rs + r_] = (s0 + s1) + (s2 + s3);
         }
     }
