@@ -796,10 +796,15 @@ int do_build(copra_b200_handle* h, const copra_b200_problem* p)
         const size_t r = F.rows, ns = F.i1 - F.i0;
         char nm[32];
         F.sMGx = r * nu * (N + 1); F.sMPhi = r * nx * ns; F.sres = r * ns; F.sE = size_t(nx) * nU; F.sf = nU;
+        // E = (M Phi)' W (M Psi + N) does not depend on p, x0 or d: one copy for the batch when A, B, M, N, w are shared
+        // (src/costFunctions.cpp:77,105,210) -- the per-instance part of the assembly is f alone
+        const bool e_shared = !F.dense && P.A.s == 0 && P.B.s == 0 && (!F.hasM || F.M.s == 0) && (!F.hasN || F.N.s == 0) && F.w.s == 0 &&
+            !getenv("COPRA_B200_NO_SHARED_HESSIAN");
+        if (e_shared) F.sE = 0;
         snprintf(nm, sizeof nm, "MGx%d", i); if ((rc = ws(h, nm, Bz * F.sMGx, &F.MGx))) return rc;
         snprintf(nm, sizeof nm, "MPhi%d", i); if ((rc = ws(h, nm, Bz * F.sMPhi, &F.MPhi))) return rc;
         snprintf(nm, sizeof nm, "res%d", i); if ((rc = ws(h, nm, Bz * F.sres, &F.res))) return rc;
-        snprintf(nm, sizeof nm, "Ec%d", i); if ((rc = ws(h, nm, Bz * F.sE, &F.E))) return rc;
+        snprintf(nm, sizeof nm, "Ec%d", i); if ((rc = ws(h, nm, (F.sE ? Bz : size_t(1)) * size_t(nx) * nU, &F.E))) return rc;
         snprintf(nm, sizeof nm, "fc%d", i); if ((rc = ws(h, nm, Bz * F.sf, &F.f))) return rc;
         F.T = F.WT = nullptr; F.sT = 0;
         if (F.dense) {
@@ -1199,14 +1204,17 @@ int copra_b200_lmpc_download(copra_b200_handle* h, int what, double* out, int me
     const size_t B = P.batch, nv = P.nvar;
     const double* src = nullptr;
     size_t count = 0;
-    if (what == COPRA_B200_GET_Q && P.sQ == 0) { // batch-invariant Hessian: one resident copy, replicated for the caller
-        const size_t bytes = nv * nv * sizeof(double);
+    // batch-invariant Hessian / per-cost E: one resident copy, replicated for the caller
+    const bool oneE = what >= COPRA_B200_GET_COST_E && what < COPRA_B200_GET_COST_E + P.ncost && P.cost[what - COPRA_B200_GET_COST_E].sE == 0;
+    if ((what == COPRA_B200_GET_Q && P.sQ == 0) || oneE) {
+        const double* one = oneE ? P.cost[what - COPRA_B200_GET_COST_E].E : P.Q;
+        const size_t cnt = oneE ? size_t(P.nx) * P.nU : nv * nv, bytes = cnt * sizeof(double);
         if (memory == COPRA_B200_DEVICE) {
-            for (size_t b = 0; b < B; ++b) CU(cudaMemcpyAsync(out + b * nv * nv, P.Q, bytes, cudaMemcpyDeviceToDevice, h->stream));
+            for (size_t b = 0; b < B; ++b) CU(cudaMemcpyAsync(out + b * cnt, one, bytes, cudaMemcpyDeviceToDevice, h->stream));
         } else {
-            CU(cudaMemcpyAsync(out, P.Q, bytes, cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaMemcpyAsync(out, one, bytes, cudaMemcpyDeviceToHost, h->stream));
             CU(cudaStreamSynchronize(h->stream));
-            for (size_t b = 1; b < B; ++b) std::memcpy(out + b * nv * nv, out, bytes);
+            for (size_t b = 1; b < B; ++b) std::memcpy(out + b * cnt, out, bytes);
         }
         return 0;
     }

@@ -536,10 +536,16 @@ __device__ __forceinline__ void dev_ef(const BuildParams& P, int b, int t, int c
 // grid = (tiles over (nx+1) nU, batch, cost); STAGED: this cost's tables are first copied to shared memory
 template <bool STAGED> __global__ void k2_assemble_ef_kernel(const __grid_constant__ BuildParams P)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y, ci = blockIdx.z;
     const CostFam& F = P.cost[ci];
     if (F.dense) return;
+    // batch-invariant E (sE == 0): instance 0 forms E and its f, every other instance only its nU entries of f
+    const bool f_only = F.sE == 0 && b > 0;
+    if (f_only) {
+        if (blockIdx.x * blockDim.x >= P.nU) return;
+        t = (t < P.nU) ? t * (P.nx + 1) + P.nx : (P.nx + 1) * P.nU; // (s, col) = (nx, t)
+    }
     Tab<STAGED> MG{ F.MGx + (long long)b * F.sMGx, 0 };
     Tab<STAGED> MPhi{ F.MPhi + (long long)b * F.sMPhi, 0 };
     Tab<STAGED> res{ F.res + (long long)b * F.sres, 0 };
