@@ -63,9 +63,11 @@ struct copra_b200_handle {
     bool factor_valid = false; // the thin solver's R^-1 of the last build is resident (re-solves skip the factorisation)
     bool rows_filled = false;  // Aeq / Aineq of the last build are materialised (the structured solver never reads them)
     bool use_thin = false;     // the last build is solved by the thin kernel (gi_thin.cuh)
+    bool gs_j_valid = false;   // the small solver's per-instance factors of the resident build are cached (re-solves load them)
     bool warm_start = false;   // copra_b200_set_warm_start: re-solves seed the active set of the previous solve
     bool warm_valid = false;   // `warm_iact` holds the active sets of the last solve of the resident build
     bool in_resolve = false;
+    bool lmpc_solve_active = false; // run_gi is called from do_solve (a resident LMPC build), not from the raw-QP entry
     bool gt_pform = false;     // ... in its shared-factor form (P = Jt Q1 kept, no factor mat-vec per pass)
     const char* solver = "";   // K5+K6 kernel(s) of the last solve
     bool nvtx_open = false;    // an NVTX stage range is open on the calling thread
@@ -414,6 +416,20 @@ int run_gi(copra_b200_handle* h, GiBatch& G)
     G.j_smem = plan.j_smem; G.s_smem = plan.s_smem; G.a_smem = plan.a_smem;
     G.ws = nullptr; G.ws_stride = plan.ws_stride;
     h->solver = plan.small ? "gi_small_kernel" : "gi_batch_kernel";
+    G.jcache = nullptr; G.jflag = nullptr; G.jmode = 0;
+    if (plan.small && h->lmpc_solve_active && !getenv("COPRA_B200_NO_FACTOR_CACHE")) {
+        // re-solves of a resident LMPC build: the first one stores every instance's factor, the following ones load it
+        // (<= 2 GB of cache; a plain build + solve pays nothing)
+        const int n2e = (G.n + 1) & ~1;
+        const size_t per = size_t((n2e % 4 == 2) ? n2e : n2e + 2) * n2e; // ld_vec2(n) * even(n), the kernel's layout of J
+        if (per * G.batch * sizeof(double) <= (size_t(2) << 30)) {
+            if ((rc = ws(h, "gs_jcache", per * G.batch, &G.jcache))) return rc;
+            if ((rc = ws(h, "gs_jflag", size_t(G.batch), &G.jflag))) return rc;
+            // (the workspace is reserved by the first solve of the build so that no re-solve allocates)
+            if (h->in_resolve) { G.jmode = h->gs_j_valid ? 2 : 1; h->gs_j_valid = true; }
+            else { G.jcache = nullptr; G.jflag = nullptr; }
+        }
+    }
     if (plan.cluster > 0) {
         int nclusters = gi_cluster_max_clusters(plan);
         if (nclusters > 0) {
@@ -844,6 +860,7 @@ int do_build(copra_b200_handle* h, const copra_b200_problem* p)
     h->built = true;
     h->factor_valid = false;
     h->warm_valid = false;
+    h->gs_j_valid = false;
     h->rows_filled = !P.skip_rows;
     return 0;
 }
@@ -890,7 +907,10 @@ int do_solve(copra_b200_handle* h, const copra_b200_results* r)
         if ((rc = ensure_rows(h))) return rc;
         G.Aeq.p = P.meq ? h->bp.Aeq : nullptr;
         G.Aineq.p = P.mineq ? h->bp.Aineq : nullptr;
-        if ((rc = run_gi(h, G))) return rc;
+        h->lmpc_solve_active = true;
+        rc = run_gi(h, G);
+        h->lmpc_solve_active = false;
+        if (rc) return rc;
     }
     if ((rc = record(h, 4))) return rc;
     const bool want_ct = !r || r->control || r->trajectory;

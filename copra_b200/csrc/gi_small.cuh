@@ -338,10 +338,14 @@ __device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, do
     // ---- 0. load (zero padded) ---------------------------------------------------------------------
     // Q and the general rows stream in with cp.async (no register staging, every copy of a thread in flight at once); the
     // factorisation starts as soon as Q has landed, the rows are only awaited before their norms are needed
-    for (int idx = tid; idx < ld * n2; idx += kSmT) {
-        const int i = idx % ld, j = idx / ld;
-        if (i < n && j < n) cp_async8(J + idx, P.Q + i + size_t(j) * n);
-        else J[idx] = (i == j && i < n2) ? 1.0 : 0.0;
+    if (P.Jin) { // receding-horizon re-solve: the factor of this instance is resident, nothing to factor
+        for (int idx = tid; idx < ld * n2; idx += kSmT) cp_async8(J + idx, P.Jin + idx);
+    } else {
+        for (int idx = tid; idx < ld * n2; idx += kSmT) {
+            const int i = idx % ld, j = idx / ld;
+            if (i < n && j < n) cp_async8(J + idx, P.Q + i + size_t(j) * n);
+            else J[idx] = (i == j && i < n2) ? 1.0 : 0.0;
+        }
     }
     cp_async_commit();
     if (mg > 0) {
@@ -374,18 +378,20 @@ __device__ inline int gs_solve(const GiView& P, const GsLayout& L, GsWork& W, do
     // the padded diagonal entry (odd n) keeps the factorisation well defined; it is zeroed afterwards
     // (the 8-pivot blocked DMMA factorisation of gi_factor.cuh was measured slower here: C2 2.03 vs 1.78 ms -- at n ~ 50 the
     // per-pivot latency chain dominates, not the sweep)
-    {   // scratch of the factorisation: vectors that hold nothing yet (red has 64 entries >= n2)
+    if (!P.Jin) { // scratch of the factorisation: vectors that hold nothing yet (red has 64 entries >= n2)
         double* const coefp[4] = { W.x, W.d, W.z, W.w };
         double* const multp[4] = { W.row, W.rowk, W.r, W.red };
         if (!gs_factor_nb<kSmFacNB>(J, ld, n, n2, coefp, multp)) fail = 2;
     }
     cp_async_wait<0>(); // the general rows have landed (also drains the copies before the buffers are reused)
     __syncthreads();
+    if (!P.Jin && P.Jflag && tid == 0) *P.Jflag = (fail == 0) ? 1 : 0;
     if (fail == 0) {
-        if (n2 > n) {
+        if (n2 > n && !P.Jin) {
             for (int i = tid; i < n2; i += kSmT) { J[n + size_t(i) * ld] = 0.0; J[i + size_t(n) * ld] = 0.0; }
             __syncthreads();
         }
+        if (P.Jout) for (int idx = tid; idx < ld * n2; idx += kSmT) P.Jout[idx] = J[idx]; // kept for the next re-solve
         // unconstrained minimiser x = J (J' (-c))
         {
             const double s = gs_col_dot<false>(J, ld, n, n2, W.v, 1);

@@ -41,6 +41,9 @@ struct GiView { // one instance, device pointers, dense column-major
     const double* bineq; // m
     const double* lb;    // n
     const double* ub;    // n
+    const double* Jin = nullptr;  // gi_small: a cached factor to load instead of factoring Q (see GiBatch::jcache)
+    double* Jout = nullptr;       // gi_small: where to store the factor
+    int* Jflag = nullptr;
 };
 
 struct GiOut {

@@ -64,6 +64,12 @@ template <bool AG, bool SG> __global__ void __launch_bounds__(kSmT, kSmMinB) gi_
         P.Aeq = B.Aeq.p ? B.Aeq.at(b) : nullptr; P.beq = B.beq.p ? B.beq.at(b) : nullptr;
         P.Aineq = B.Aineq.p ? B.Aineq.at(b) : nullptr; P.bineq = B.bineq.p ? B.bineq.at(b) : nullptr;
         P.lb = B.lb.at(b); P.ub = B.ub.at(b);
+        if (B.jmode) {
+            double* jc = B.jcache + (long long)b * L.ld * L.n2;
+            P.Jin = (B.jmode == 2 && B.jflag[b] == 1) ? jc : nullptr;
+            P.Jout = P.Jin ? nullptr : jc;
+            P.Jflag = B.jflag + b;
+        }
         GiOut O;
         O.x = B.x ? B.x + (long long)b * B.n : nullptr;
         O.status = B.status ? B.status + b : nullptr;

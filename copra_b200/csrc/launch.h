@@ -19,6 +19,12 @@ struct GiBatch {
     double vsmall;
     int max_iter;
     int j_smem, s_smem, a_smem;
+    // gi_small_kernel only -- the factor J = R^-1 of every instance kept across a receding-horizon re-solve (the Hessian does
+    // not change with x0): jmode 1 = store J (and jflag = 1 when Q was positive definite) after factoring, 2 = load it instead
+    // of factoring (instances whose jflag is 0 factor again), 0 = off.  jcache: ld_vec2(n) * even(n) doubles per instance.
+    double* jcache;
+    int* jflag;
+    int jmode;
 };
 
 struct GiPlan {
