@@ -163,7 +163,7 @@ __host__ __device__ inline GtLayout gt_layout(int n, int meq, int m, int tab_dou
     L.oRed = o; o += 10 * kMaxWarps;
     {
         const size_t trap = (size_t(2 * (threads / 32) + (n + 63) / 64 + 2) << 6) + 2 * size_t(threads);
-        const size_t pass = 3 * size_t(threads); // gt_pass_rows: P partials (2T) + S partials (T)
+        const size_t pass = 6 * size_t(threads); // gt_pass_rows: P partials (2T) + S partials (T); twice that for gt_pass_rows2
         L.oPart = o; o += trap > pass ? trap : pass;
     }
     L.oQ1 = o; o += size_t(q1s) * np;
@@ -600,6 +600,106 @@ __device__ __forceinline__ void gt_pass_rows(const GtWork& W, int ld, int q1s, i
     }
 }
 
+// Two right-hand sides in one sweep (the warm-start seed adds its rows two at a time): out0[c] = P[:, c] . v0, out1[c] = P[:, c] . v1
+__device__ __forceinline__ void gt_q1_col_dots2(const GtWork& W, int ld, int q1s, int nact, const double* __restrict__ v0,
+    const double* __restrict__ v1, double* __restrict__ out0, double* __restrict__ out1)
+{
+    const int lane = lane_id(), wp = warp_id(), nw = blockDim.x >> 5;
+    const int g8 = lane >> 3, l8 = lane & 7;
+    for (int cb = 4 * wp; cb < nact; cb += 4 * nw) {
+        const int c = cb + g8;
+        const bool on = c < nact;
+        const double* col = (c < q1s ? W.Q1s : W.Q1) + size_t(on ? c : 0) * ld;
+        double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
+        if (on) {
+            int k = 2 * l8;
+            for (; k + 16 < ld; k += 32) {
+                const double2 a0 = *reinterpret_cast<const double2*>(col + k), a1 = *reinterpret_cast<const double2*>(col + k + 16);
+                const double2 x0 = *reinterpret_cast<const double2*>(v0 + k), x1 = *reinterpret_cast<const double2*>(v0 + k + 16);
+                const double2 y0 = *reinterpret_cast<const double2*>(v1 + k), y1 = *reinterpret_cast<const double2*>(v1 + k + 16);
+                s0 = fma(a0.y, x0.y, fma(a0.x, x0.x, s0)); s1 = fma(a1.y, x1.y, fma(a1.x, x1.x, s1));
+                t0 = fma(a0.y, y0.y, fma(a0.x, y0.x, t0)); t1 = fma(a1.y, y1.y, fma(a1.x, y1.x, t1));
+            }
+            if (k < ld) {
+                const double2 a0 = *reinterpret_cast<const double2*>(col + k);
+                const double2 x0 = *reinterpret_cast<const double2*>(v0 + k), y0 = *reinterpret_cast<const double2*>(v1 + k);
+                s0 = fma(a0.y, x0.y, fma(a0.x, x0.x, s0)); t0 = fma(a0.y, y0.y, fma(a0.x, y0.x, t0));
+            }
+        }
+        double qa = s0 + s1, qb = t0 + t1;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) { qa += __shfl_xor_sync(0xffffffffu, qa, o); qb += __shfl_xor_sync(0xffffffffu, qb, o); }
+        if (on && l8 == 0) { out0[c] = qa; out1[c] = qb; }
+    }
+}
+
+// w0 = P v0, w1 = P v1, r0 = S v0, r1 = S v1 in one sweep over P and S (layout and tiling of gt_pass_rows; `part` holds
+// 6 * blockDim.x doubles).  ONE __syncthreads inside; the caller syncs before reading.
+__device__ __forceinline__ void gt_pass_rows2(const GtWork& W, int ld, int q1s, int nact, const double* __restrict__ v0,
+    const double* __restrict__ v1, double* __restrict__ w0, double* __restrict__ w1, const double* __restrict__ S, size_t lds,
+    double* __restrict__ r0, double* __restrict__ r1, double* __restrict__ part)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int pairs = ld >> 1, rp = max(32, round32(pairs)), G = max(1, T / rp);
+    double* pQ0 = part;
+    double* pQ1 = part + 2 * size_t(T);
+    double* pS0 = part + 4 * size_t(T);
+    double* pS1 = part + 5 * size_t(T);
+    {
+        const int g = tid / rp, pr = tid - g * rp;
+        if (g < G && pr < pairs) {
+            double2 a = make_double2(0.0, 0.0), b2 = a, c2 = a, d2 = a;
+            int c = g;
+            for (; c + G < nact; c += 2 * G) {
+                const double2 p0 = *reinterpret_cast<const double2*>((c < q1s ? W.Q1s : W.Q1) + size_t(c) * ld + 2 * pr);
+                const double2 p1 = *reinterpret_cast<const double2*>((c + G < q1s ? W.Q1s : W.Q1) + size_t(c + G) * ld + 2 * pr);
+                const double x0 = v0[c], x1 = v0[c + G], y0 = v1[c], y1 = v1[c + G];
+                a.x = fma(p0.x, x0, a.x); a.y = fma(p0.y, x0, a.y); b2.x = fma(p1.x, x1, b2.x); b2.y = fma(p1.y, x1, b2.y);
+                c2.x = fma(p0.x, y0, c2.x); c2.y = fma(p0.y, y0, c2.y); d2.x = fma(p1.x, y1, d2.x); d2.y = fma(p1.y, y1, d2.y);
+            }
+            if (c < nact) {
+                const double2 p0 = *reinterpret_cast<const double2*>((c < q1s ? W.Q1s : W.Q1) + size_t(c) * ld + 2 * pr);
+                const double x0 = v0[c], y0 = v1[c];
+                a.x = fma(p0.x, x0, a.x); a.y = fma(p0.y, x0, a.y); c2.x = fma(p0.x, y0, c2.x); c2.y = fma(p0.y, y0, c2.y);
+            }
+            *reinterpret_cast<double2*>(pQ0 + 2 * (g * rp + pr)) = make_double2(a.x + b2.x, a.y + b2.y);
+            *reinterpret_cast<double2*>(pQ1 + 2 * (g * rp + pr)) = make_double2(c2.x + d2.x, c2.y + d2.y);
+        }
+    }
+    const int rs = max(32, round32(nact)), GS = max(1, T / rs);
+    {
+        const int g = tid / rs, r_ = tid - g * rs;
+        if (g < GS && r_ < nact) {
+            const double* sr = S + W.rowmap[r_];
+            double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
+            int c = g;
+            for (; c + GS < nact; c += 2 * GS) {
+                const double m0 = sr[size_t(c) * lds], m1 = sr[size_t(c + GS) * lds];
+                s0 = fma(m0, v0[c], s0); s1 = fma(m1, v0[c + GS], s1); t0 = fma(m0, v1[c], t0); t1 = fma(m1, v1[c + GS], t1);
+            }
+            if (c < nact) { const double m0 = sr[size_t(c) * lds]; s0 = fma(m0, v0[c], s0); t0 = fma(m0, v1[c], t0); }
+            pS0[g * rs + r_] = s0 + s1;
+            pS1[g * rs + r_] = t0 + t1;
+        }
+    }
+    __syncthreads();
+    if (tid < pairs) {
+        double2 a = *reinterpret_cast<const double2*>(pQ0 + 2 * tid), b2 = *reinterpret_cast<const double2*>(pQ1 + 2 * tid);
+        for (int k = 1; k < G; ++k) {
+            const double2 a1 = *reinterpret_cast<const double2*>(pQ0 + 2 * (k * rp + tid)), b1 = *reinterpret_cast<const double2*>(pQ1 + 2 * (k * rp + tid));
+            a.x += a1.x; a.y += a1.y; b2.x += b1.x; b2.y += b1.y;
+        }
+        *reinterpret_cast<double2*>(w0 + 2 * tid) = a;
+        *reinterpret_cast<double2*>(w1 + 2 * tid) = b2;
+    }
+    if (tid < nact) {
+        double s = pS0[tid], t = pS1[tid];
+        for (int k = 1; k < GS; ++k) { s += pS0[k * rs + tid]; t += pS1[k * rs + tid]; }
+        r0[tid] = s;
+        r1[tid] = t;
+    }
+}
+
 // Fused block reduction of a pass: four sums and the step-length arg-min behind ONE barrier (every warp finishes the
 // reduction redundantly).  `scr` (5 x kMaxWarps doubles) / `scri` must not be touched by anything else between two barriers.
 struct GtPassRed { double dd, zz, za, dn; MinIdx t1; };
@@ -1016,16 +1116,15 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
         GT_T(0);
 
         // ---- the two updates of the factorisation (shared by the iterations and the warm start) --------------------------------
-        auto add_column = [&](int nvl, double dd) {
+        auto add_column_from = [&](int nvl, double dd, const double* zsrc, const double* rsrc) {
             // ---- add constraint nvl: Q1 gains zt / delta, S the column [-r/delta ; 1/delta] ----------------------
             const double delta = sqrt(dd), inv = 1.0 / delta;
             double* qc = q1col(nact);
-            const double* src = pform ? W.z : W.zt; // shared-factor form: the column of P = Jt Q1 is z / |zt|
-            for (int j = tid * cl.size() + cl.rank(); j < np; j += T * cl.size()) qc[j] = (j < n) ? src[j] * inv : 0.0;
+            for (int j = tid * cl.size() + cl.rank(); j < np; j += T * cl.size()) qc[j] = (j < n) ? zsrc[j] * inv : 0.0;
             const int newrow = W.rowmap[nact];
             if (cl.rank() == 0) {
                 for (int i = tid; i < nact; i += T) {
-                    S[W.rowmap[i] + size_t(nact) * ldn] = -W.r[i] * inv;
+                    S[W.rowmap[i] + size_t(nact) * ldn] = -rsrc[i] * inv;
                     S[newrow + size_t(i) * ldn] = 0.0;
                 }
                 if (tid == 0) S[newrow + size_t(nact) * ldn] = inv;
@@ -1037,6 +1136,7 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
             ++nact;
             cl.sync();
         };
+        auto add_column = [&](int nvl, double dd) { add_column_from(nvl, dd, pform ? W.z : W.zt, W.r); }; // pform: the column of P is z / |zt|
         auto drop_constraint = [&](int p) {
             cl.sync(); // (cluster: every replica has finished reading r / w before the stores below replace them)
                         const int dropped = (tid == 0) ? W.iact[p] - 1 : 0;
@@ -1102,21 +1202,19 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
             const int* wl = B.warm + (long long)b * n;
             for (int k = tid; k < n; k += T) W.d[k] = W.x[k]; // x_unc (W.d is otherwise unused in this form)
             __syncthreads();
-            for (int wi = 0; wi < n && nact < n; ++wi) {
-                const int id = wl[wi];
-                if (id <= 0) break;
-                const int nvl = id - 1;
-                if (nvl < meq || nvl >= q || W.active[nvl]) continue; // equalities enter through the regular iterations
-                int bj = -1, supp = n;
-                double bsign = 0.0;
+            // The seed rows enter TWO at a time: one sweep over P forms both d1 = P'a, one sweep over P and S both w = P d1 and
+            // r = S d1; the second row is then made orthogonal to the first new column in closed form:
+            //   g = p1'a2 = (z1'a2) / |zt1| ,  z2 = z2' - g p1 ,  |zt2|^2 = a2'z2' - g^2 ,  d1_2 <- [d1_2 ; g] ,  r2 <- [r2 - g r1 / |zt1| ; g / |zt1|]
+            // Storage: row 1 uses av / z / w / d1 / r as a regular pass does, row 2 uses xt / zt / v / u / x (x_unc sits in W.d).
+            auto seed_normal = [&](int nvl, double* av, double* hz) { // av = signed normal (explicit also for bound rows), hz = H a
                 if (nvl < mg) {
                     int fi, step, line;
                     gt_locate(B, nvl, fi, step, line);
                     const GtFam& F = B.fam[fi];
-                    supp = min(step + 1, B.N) * B.nu;
+                    const int supp = min(step + 1, B.N) * B.nu;
                     for (int k = tid; k < np; k += T) {
                         const int j = k / B.nu, bb = k - j * B.nu;
-                        W.av[k] = (k < supp) ? -gt_tab(B, W.tab, F, line, bb, step - j) : 0.0;
+                        av[k] = (k < supp) ? -gt_tab(B, W.tab, F, line, bb, step - j) : 0.0;
                     }
                     const double* Ef = F.E.p ? F.E.at(b) : nullptr;
                     const double* Gf = (F.G.p && step < B.N) ? F.G.at(b) : nullptr;
@@ -1126,36 +1224,106 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
                         double acc = 0.0;
                         if (Ef) for (int e = 0; e < B.nx; ++e) acc = fma(Ef[line + e * F.rows], __ldg(dp + k + size_t(e) * ld), acc);
                         if (Gf) for (int e = 0; e < B.nu; ++e) acc = fma(Gf[line + e * F.rows], __ldg(jp + k + size_t(e) * ld), acc);
-                        W.z[k] = -acc;
+                        hz[k] = -acc;
                     }
                 } else {
-                    const int j = nvl - mg;
-                    if (j < n) { bj = j; bsign = -1.0; }
-                    else { bj = j - n; bsign = 1.0; }
+                    const int j = nvl - mg, bj = j < n ? j : j - n;
+                    const double bsign = j < n ? -1.0 : 1.0;
                     const double* hp = B.Hm + size_t(bj) * ld;
-                    for (int k = tid; k < n; k += T) W.z[k] = bsign * __ldg(hp + k);
+                    for (int k = tid; k < np; k += T) av[k] = (k == bj) ? bsign : 0.0;
+                    for (int k = tid; k < n; k += T) hz[k] = bsign * __ldg(hp + k);
                 }
+            };
+            auto next_seed = [&](int& wi) -> int { // next usable entry of the previous active set (uniform over the CTA), -1: none
+                for (; wi < n; ++wi) {
+                    const int id = wl[wi];
+                    if (id <= 0) { wi = n; return -1; }
+                    const int nvl = id - 1;
+                    if (nvl < meq || nvl >= q || W.active[nvl]) continue; // equalities enter through the regular iterations
+                    ++wi;
+                    return nvl;
+                }
+                return -1;
+            };
+            double* scr6 = W.red + 4 * kMaxWarps; // 5 x kMaxWarps doubles: the five sums below
+            for (int wi = 0; nact < n;) {
+                const int s1 = next_seed(wi);
+                if (s1 < 0) break;
+                int wi2 = wi;
+                int s2 = (nact + 1 < n) ? next_seed(wi2) : -1;
+                if (s2 == s1) s2 = -1;
+                seed_normal(s1, W.av, W.z);
+                if (s2 >= 0) seed_normal(s2, W.xt, W.zt);
                 __syncthreads();
                 if (nact > 0) {
-                    if (bj >= 0) { for (int c = tid; c < nact; c += T) W.d1[c] = bsign * q1col(c)[bj]; }
-                    else gt_q1_col_dots(cl, W, n, ld, q1s, nact, W.av, W.d1, supp);
-                    __syncthreads();
-                    gt_pass_rows(W, ld, q1s, nact, W.d1, W.w, S, ldn, W.r, W.part);
+                    if (s2 >= 0) {
+                        gt_q1_col_dots2(W, ld, q1s, nact, W.av, W.xt, W.d1, W.u);
+                        __syncthreads();
+                        gt_pass_rows2(W, ld, q1s, nact, W.d1, W.u, W.w, W.v, S, ldn, W.r, W.x, W.part);
+                    } else {
+                        gt_q1_col_dots(cl, W, n, ld, q1s, nact, W.av, W.d1);
+                        __syncthreads();
+                        gt_pass_rows(W, ld, q1s, nact, W.d1, W.w, S, ldn, W.r, W.part);
+                    }
                     __syncthreads();
                 }
-                double a_za = 0.0, a_dn = 0.0;
+                // z1 = h1 - w1, z2' = h2 - w2 and the five inner products
+                double c11 = 0.0, c12 = 0.0, c22 = 0.0, e1 = 0.0, e2 = 0.0;
                 for (int k = tid; k < n; k += T) {
-                    const double ak = (bj >= 0) ? (k == bj ? bsign : 0.0) : W.av[k];
-                    double zk = W.z[k];
-                    a_dn = fma(ak, zk, a_dn);
-                    if (nact > 0) { zk -= W.w[k]; W.z[k] = zk; }
-                    a_za = fma(ak, zk, a_za);
+                    const double a1 = W.av[k];
+                    double z1 = W.z[k];
+                    e1 = fma(a1, z1, e1);
+                    if (nact > 0) { z1 -= W.w[k]; W.z[k] = z1; }
+                    c11 = fma(a1, z1, c11);
+                    if (s2 >= 0) {
+                        const double a2 = W.xt[k];
+                        double z2 = W.zt[k];
+                        e2 = fma(a2, z2, e2);
+                        if (nact > 0) { z2 -= W.v[k]; W.zt[k] = z2; }
+                        c22 = fma(a2, z2, c22);
+                        c12 = fma(a2, z1, c12);
+                    }
                 }
-                MinIdx none; none.v = 0.0; none.i = -1;
-                const GtPassRed pr = gt_pass_reduce(0.0, 0.0, a_za, a_dn, none, W.red + 4 * kMaxWarps, W.redi + kMaxWarps);
-                if (pr.za > 1e-10 * pr.dn) add_column(nvl, pr.za); // ends with a barrier
-                else __syncthreads();
+                {
+                    const int lane = lane_id(), wpi = warp_id(), nw = T >> 5;
+                    c11 = warp_sum(c11); c12 = warp_sum(c12); c22 = warp_sum(c22); e1 = warp_sum(e1); e2 = warp_sum(e2);
+                    if (lane == 0) { scr6[wpi] = c11; scr6[kMaxWarps + wpi] = c12; scr6[2 * kMaxWarps + wpi] = c22; scr6[3 * kMaxWarps + wpi] = e1; scr6[4 * kMaxWarps + wpi] = e2; }
+                    __syncthreads();
+                    const bool on = lane < nw;
+                    c11 = warp_sum(on ? scr6[lane] : 0.0); c12 = warp_sum(on ? scr6[kMaxWarps + lane] : 0.0);
+                    c22 = warp_sum(on ? scr6[2 * kMaxWarps + lane] : 0.0); e1 = warp_sum(on ? scr6[3 * kMaxWarps + lane] : 0.0);
+                    e2 = warp_sum(on ? scr6[4 * kMaxWarps + lane] : 0.0);
+                }
+                const bool ok1 = c11 > 1e-10 * e1;
+                const int nact0 = nact;
+                double g = 0.0, inv1 = 0.0;
+                if (ok1) {
+                    inv1 = 1.0 / sqrt(c11);
+                    g = c12 * inv1;
+                    add_column_from(s1, c11, W.z, W.r); // ends with a barrier
+                } else __syncthreads();
+                if (s2 >= 0) {
+                    const double dd2 = ok1 ? c22 - g * g : c22;
+                    // row 2 enters in the same round only when the closed-form correction did not cancel most of it; otherwise
+                    // it is left for the next round (wi is not advanced past it), where it gets its own exact projection
+                    if (dd2 > 1e-10 * e2 && dd2 > 0.25 * c22) {
+                        if (ok1) {
+                            for (int k = tid; k < n; k += T) W.zt[k] -= (g * inv1) * W.z[k];
+                            for (int i = tid; i < nact0; i += T) W.x[i] -= (g * inv1) * W.r[i];
+                            if (tid == 0) W.x[nact0] = g * inv1;
+                            __syncthreads();
+                        }
+                        add_column_from(s2, dd2, W.zt, W.x); // ends with a barrier
+                        wi = wi2;
+                    } else if (dd2 <= 1e-10 * e2 && !(ok1 && dd2 <= 0.25 * c22 && c22 > 1e-10 * e2)) {
+                        wi = wi2; // dependent on the rows already in: skipped for good
+                    }
+                }
             }
+            for (int k = tid; k < n; k += T) W.x[k] = W.d[k]; // x_unc back in place (W.x was scratch above)
+            if (tid == 0) { W.u[n] = 0.0; }
+            for (int k = tid; k < n; k += T) W.u[k] = 0.0;
+            __syncthreads();
             if (nact > 0) {
                 // slacks of the seeded rows at x_unc (W.x still holds it)
                 if (use_ss) gt_products_ss(cl, B, W, [&](int row, double v) { cl.put(W.sl + row, v); });
