@@ -46,6 +46,11 @@ namespace cg = cooperative_groups;
 //            address of every CTA (DSMEM) with put(), and one cluster barrier publishes them.  All CTAs run the same control
 //            flow on bitwise identical replicas, so no decision is ever exchanged.  Q1 and S live in global memory (L2) and are
 //            written in disjoint pieces; the cluster barrier (release / acquire at cluster scope) orders those writes too.
+//            INTERVAL RULE that makes the remote stores safe: between two consecutive cluster barriers a replicated buffer is
+//            either only read or only written through put() -- never both -- because CTAs drift apart by up to one interval
+//            (local __syncthreads do not align them).  Hence the cluster barrier after the load phase (no put() may land before
+//            a replica is initialised), at the start of a drop (every replica has finished reading r / w of the step update)
+//            and after every phase whose outputs are put().
 struct GtSolo {
     static constexpr bool multi = false;
     __device__ __forceinline__ int rank() const { return 0; }
