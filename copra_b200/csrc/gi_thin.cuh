@@ -1000,7 +1000,8 @@ __device__ inline int gt_solve(const CL& cl, const GtBatch& B, const GtWork& W, 
 {
     const int n = B.n, meq = B.meq, m = B.m, mg = meq + m, q = mg + 2 * n, np = gt_even(n);
     const int tid = threadIdx.x, T = blockDim.x;
-    const int ld = B.ld, q1s = B.q1s;
+    const int ld = B.ld;
+    const int q1s = (FORM >= 1) ? 0 : B.q1s; // shared-factor form: P lives in the global workspace only (the host plans q1s = 0)
     const size_t ldn = size_t(n);
     const double* __restrict__ Jt = B.Jt.at(b);
     const double* __restrict__ JtT = B.JtT.at(b);

@@ -112,6 +112,7 @@ GtPlan gt_plan(const GtShape& sh, int batch, int sms, size_t smem_optin)
     int q1s = budget > base ? int((budget - base) / (size_t(sh.ld) * sizeof(double))) : 0;
     q1s = std::min(q1s, sh.n);
     q1s = std::min(q1s, std::max(0, gt_env_int("COPRA_B200_THIN_Q1S", sh.n)));
+    if (sh.pform) q1s = 0; // the shared-factor kernels are compiled without the shared-memory head of P
     p.q1s = q1s;
     p.smem_bytes = gt_layout(sh.n, sh.meq, sh.m, sh.tab_doubles, p.threads, q1s, sh.ss_doubles).bytes;
     p.per_sm = per_sm;
